@@ -1,0 +1,138 @@
+"""Pin the oracle (oracle/np_oracle.py) against every golden vector produced by the reference's own
+modules (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+from shmfast import synth
+
+
+def _rel(a, b, floor=1e-6):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+@pytest.mark.parametrize("stage", ["4dof", "openlab", "1dof"])
+@pytest.mark.parametrize("scale", [1, 3])
+def test_vae_matches_reference_module(golden_dir, stage, scale):
+    g = np.load(golden_dir / f"synth_vae_{stage}_s{scale}.npz")
+    s = synth.STAGES[stage]
+    seed, N = int(g["seed"]), int(g["N"])
+    sd = synth.stage_vae_weights(stage, seed=seed, scale=float(g["scale"]))
+    X = synth.windows(N, s["T"], s["D"], seed=seed, amp=1.0 if scale == 1 else 2.5)
+    eps = synth.eps(N, s["Z"], seed=seed)
+    recon, mu, lv = O.vae_forward(sd, X, eps, np.float32)
+    score = O.mse_score(X, recon)
+    # fp32 restatement vs the reference's fp32 module: summation-order noise only
+    assert np.allclose(mu, g["mu"], rtol=2e-5, atol=2e-6)
+    assert np.allclose(lv, g["logvar"], rtol=2e-5, atol=2e-6)
+    assert np.allclose(recon[:8], g["recon"], rtol=1e-4, atol=2e-5)
+    assert _rel(score, g["score"]) < 1e-5
+    assert np.allclose(recon.astype(np.float64).sum(axis=(1, 2)), g["recon_checksum"], rtol=0, atol=5e-3)
+    # fp64 restatement agrees too (the truth the tolerance studies use)
+    recon64, _, _ = O.vae_forward(sd, X, eps, np.float64)
+    assert _rel(O.mse_score(X.astype(np.float64), recon64), g["score"]) < 1e-5
+
+
+def test_cnn4dof_matches_reference_module(golden_dir):
+    g = np.load(golden_dir / "synth_cnn4dof.npz")
+    sd = synth.cnn4dof_weights(seed=int(g["seed"]))
+    z = synth.windows(int(g["N"]), 100, 12, seed=21)
+    rec = synth.windows(int(g["N"]), 100, 12, seed=22, amp=0.7)
+    logits = O.cnn4dof_forward(sd, O.cnn4dof_inputs(z, rec))
+    assert np.allclose(logits, g["logits"], rtol=1e-4, atol=1e-4)
+    assert np.array_equal(np.argmax(logits, 1), np.argmax(g["logits"], 1))
+
+
+def test_cnnol_matches_reference_module(golden_dir):
+    g = np.load(golden_dir / "synth_cnnol.npz")
+    sd = synth.cnnol_weights(seed=int(g["seed"]))
+    x = synth.windows(int(g["N"]), 200, 4, seed=31, amp=1.5)[:, None]
+    logits = O.cnnol_forward(sd, x)
+    assert np.allclose(logits, g["logits"], rtol=1e-4, atol=1e-4)
+
+
+def test_openlab_real_windows(golden_dir):
+    g = np.load(golden_dir / "openlab_real_windows.npz")
+    vae_sd = synth.stage_vae_weights("openlab", seed=int(g["seed"]), scale=2.0)
+    cnn_sd = synth.cnnol_weights(seed=int(g["seed"]))
+    eps = synth.eps(g["X_clean"].shape[0], 8, seed=int(g["seed"]))
+    assert np.isnan(g["X_raw"]).any()          # the NaN path is exercised
+    r = O.hybrid_openlab(vae_sd, cnn_sd, g["X_clean"], g["X_raw"], g["channels_idx"], g["vae_mu"], g["vae_sd"],
+                         g["cnn_mu"], g["cnn_sd"], eps, float(g["vae_thr"]), float(g["cnn_thr"]))
+    assert _rel(r["score"], g["score"]) < 1e-5
+    assert np.array_equal(r["mask"], g["mask"])
+    assert np.allclose(r["logits"], g["logits"], rtol=1e-4, atol=1e-4)
+    assert np.allclose(r["prob"], g["prob"], atol=1e-5)
+    assert np.array_equal(r["pred"], g["pred"])
+
+
+def test_onedof_stitch_rmse(golden_dir):
+    g = np.load(golden_dir / "onedof_seen.npz")
+    sd = synth.stage_vae_weights("1dof", seed=int(g["seed"]), scale=2.0)
+    data_t, mean, std = g["data_t"], g["mean"], g["std"]
+    norm = O.standardize_series_1dof(data_t, mean, std)
+    W = O.make_windows_1dof(norm, 80, 1)
+    assert W.shape[0] == int(g["n_windows"])
+    xb = W.astype(np.float32)
+    assert np.array_equal(xb[:4], g["windows_f32_head"])
+    eps = synth.eps(W.shape[0], 5, seed=int(g["seed"]))
+    recon, mu, _ = O.vae_forward(sd, xb, eps, np.float32)
+    assert np.allclose(mu, g["mu"], rtol=2e-5, atol=2e-6)
+    series = O.destandardize(O.stitch_windows(recon, norm.shape[0], 1), mean, std)
+    assert np.allclose(series, g["recon_series"], rtol=1e-4, atol=1e-5)
+    rm = O.segment_rmse(data_t, series, 100)
+    assert np.allclose(rm, g["segment_rmse"], rtol=1e-4)
+
+
+def test_trained_4dof_pipeline(golden_dir):
+    p = golden_dir / "trained_4dof.npz"
+    if not p.exists():
+        pytest.skip("trained fixture not generated")
+    g = np.load(p)
+    vae_sd = {k[4:]: g[k] for k in g.files if k.startswith("vae.")}
+    cnn_sd = {k[4:]: g[k] for k in g.files if k.startswith("cnn.")}
+    Z = O.normalize_windows_4dof(g["W"], g["mean"], O.guard_std_4dof(g["std"]))
+    assert np.array_equal(Z, g["Z"])
+    N = Z.shape[0]
+    eps1 = synth.eps(N, 16, seed=41)
+    eps2 = synth.eps(int(g["idx"].size), 16, seed=42)
+    r = O.hybrid_4dof(vae_sd, cnn_sd, Z, eps1, eps2, float(g["thr"]))
+    assert _rel(r["score"], g["score"]) < 2e-5
+    assert np.array_equal(r["mask"], g["mask"])
+    assert np.array_equal(r["idx"], g["idx"])
+    # fp32 re-association alone moves these logits ~3e-5 relative
+    assert np.allclose(r["logits"], g["logits"], rtol=2e-4, atol=2e-4)
+    assert np.array_equal(r["y_pred"][g["idx"]], g["y_pred"])
+    assert np.allclose(r["p_struct"][g["idx"]], g["p_struct"], atol=1e-4)
+
+
+def test_windowing_semantics():
+    X = synth.series(301, 12, seed=3)
+    W = O.make_windows(X, 100, 1)
+    assert W.shape == (202, 100, 12)                    # 202 test windows per 4DOF file
+    assert np.array_equal(W[5, 7], X[12])
+    assert O.make_windows(X[:50], 100, 1).shape == (0, 100, 12)
+    W2 = O.make_windows(X, 200, 20)
+    assert W2.shape[0] == O.n_windows(301, 200, 20) == 6
+    assert np.array_equal(O.slice_frac(np.arange(1001)[:, None], (0.7, 1.0))[:, 0], np.arange(700, 1001))
+    with pytest.raises(ValueError):
+        O.make_windows_1dof(X[:10], 80, 1)
+
+
+def test_normalisation_guards():
+    mean, std = synth.stats(12, seed=1, zero_std_channel=3)
+    W = synth.windows(4, 100, 12, seed=1)
+    W[0, 0, 0] = np.nan; W[1, 2, 5] = np.inf
+    Z = O.normalize_windows_4dof(W, mean, O.guard_std_4dof(std))
+    assert Z[0, 0, 0] == 0 and Z[1, 2, 5] == 0 and np.isfinite(Z).all()
+    assert np.allclose(Z[2, 3, 3], (W[2, 3, 3] - mean[3]) / np.float32(1e-6))
+    Xn = O.standardize_openlab(W * 20, mean, np.where(std < 1e-12, 1.0, std).astype(np.float32), 10.0)
+    assert Xn.max() <= 10 and Xn.min() >= -10 and Xn[0, 0, 0] == 0
+
+
+def test_flag_compact_strict_fp32():
+    s = np.array([0.5, 1.2814044, 1.2814045, 3.0, np.float32(1.2814043760299683)], dtype=np.float32)
+    mask, idx = O.flag_compact(s, 1.2814043760299683)
+    assert mask.tolist() == [False, False, True, True, False] or mask.tolist() == [False, False, True, True, False]
+    assert idx.tolist() == np.where(mask)[0].tolist()
