@@ -1,0 +1,335 @@
+#!/usr/bin/env python3
+"""Headline benchmark: hybrid window scoring throughput (windows/s), BASELINE.json's metric.
+
+    python bench.py --gpus N --steps K --warmup W [--impl shmfast|reference] [--workload ...]
+
+A "step" is one pass of the hot path over one batch of synthetic 4DOF windows per GPU:
+fused gather+normalise from the raw series -> LSTM-VAE score -> stored-threshold compare + ascending
+compaction -> second VAE pass on the flagged windows -> residual stack -> CNN -> labels
+(06_test_full_pipeline.py:327-383), with the threshold calibrated as 04_vae_thresholding.py does (P99 of
+a 2,010-window calibration set => ~1 % flagged).  This is BASELINE.json configs[1] (4DOF scoring +
+thresholding on 1xB200) extended by the CNN attribution the metric names (configs[2] per GPU).
+
+`value`      device-resident throughput: inputs (series, eps) already in HBM, CUDA-event timed per step.
+`e2e`        the same through the public API with HOST buffers: pinned series H2D every step, eps drawn on
+             the device like the reference's forward() does, scores/flags/labels D2H every step.
+`roofline`   the dominant kernel (fused VAE scorer): algorithmic FLOPs / CUDA-event launch time vs the
+             measured dense bf16 peak (MEASURED_PEAKS.json).
+`cpu_baseline` / `--impl reference`: oracle/torch_port.py (the reference's wiring on torch.nn CPU kernels)
+             timed on the host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+PKG = ROOT / "hybrid-vae-cnn-for-shm_b200"
+for p in (str(ROOT), str(PKG)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "windows/sec (VAE score + CNN attribution)"
+# algorithmic work per window, SURVEY.md section 8(d) / BASELINE.md section 3
+FLOP_PER_WINDOW = {"4dof": 80_322_560, "openlab": 13_527_040, "1dof": 4_248_512}
+CNN_FLOP_PER_FLAGGED = {"4dof": 4_070_912, "openlab": 133_851_648}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["shmfast", "reference"], default="shmfast")
+    ap.add_argument("--workload", choices=["4dof_hybrid", "4dof_score"], default="4dof_hybrid")
+    ap.add_argument("--windows", type=int, default=1 << 20, help="windows per GPU per step")
+    ap.add_argument("--engine", choices=["auto", "fp32", "tc"], default="auto")
+    ap.add_argument("--cpu-sample", type=int, default=16384, help="windows per CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm_gbs=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]), tf_sust=float(d["bf16_tflops_sustained"]),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")      # B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(dev_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.strip().lower() == "active"})
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+def synth_problem(n_windows: int, seed: int):
+    from shmfast import synth
+    from shmfast.pipeline import guard_std_4dof
+    s = synth.STAGES["4dof"]
+    series = synth.series(n_windows + s["T"] - 1, s["D"], seed=seed)
+    mean, std = synth.stats(s["D"], seed=0)
+    return s, series, mean, guard_std_4dof(std)
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: oracle/torch_port.py on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_port_run(sample: int, steps: int, warmup: int, thr: float | None, workload: str):
+    from oracle import torch_port as TP     # the one place bench.py executes oracle/: as the timed CPU baseline
+    from shmfast import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    s, series, mean, std = synth_problem(sample, seed=123)
+    vae = TP.VaePort(synth.stage_vae_weights("4dof", seed=0))
+    cnn = TP.Cnn4dofPort(synth.cnn4dof_weights(seed=0))
+    torch.manual_seed(42)
+    if thr is None:
+        cal = TP.hybrid_4dof(vae, cnn, synth_problem(2010, seed=7)[1], mean, std, float("inf"))
+        thr = float(np.percentile(cal["score"], 99.0))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        r = TP.hybrid_4dof(vae, cnn, series, mean, std, thr if workload == "4dof_hybrid" else float("inf"))
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return dict(value=sample / (ms / 1e3), ms_per_step=ms, cores=cores, threads=torch.get_num_threads(),
+                sample=f"{sample} windows of the {workload} step per timed pass (series gather + normalise + VAE score, batch 512"
+                       f" + threshold + second pass/CNN on the flagged), torch.nn CPU kernels, {steps} passes after {warmup} warm-up",
+                flagged=int(r["idx"].size), thr=thr)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = min(a.cpu_sample, a.windows)
+    r = cpu_port_run(sample, a.steps, a.warmup, None, a.workload)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "windows/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": a.workload, "windows_per_step": sample, "T": 100, "D": 12, "H": 128, "Z": 16, "L": 2,
+                   "note": "reference CPU path (torch.nn on host cores) on a bounded sample of the GPU arm's workload"},
+        "cpu_baseline": {"value": r["value"], "unit": "windows/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# the product arm
+# ----------------------------------------------------------------------------------------------
+def run_shmfast(a):
+    import torch.distributed as dist
+
+    from shmfast import ops, synth
+    from shmfast.pipeline import Hybrid4dof
+    from shmfast.shard import max_over_ranks, sum_over_ranks
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl shmfast needs a CUDA device: libshmfast has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", init_method="env://", device_id=dev)
+    if world != a.gpus and rank == 0:
+        print(f"[bench] note: --gpus {a.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    engine = {"auto": ops.ENGINE_AUTO, "fp32": ops.ENGINE_FP32, "tc": ops.ENGINE_TC_BF16X3}[a.engine]
+    N = a.windows
+    s, series_h, mean, std = synth_problem(N, seed=100 + rank)            # each rank scores its own window range
+    T, D, Z = s["T"], s["D"], s["Z"]
+    vae = ops.VaeScorer(synth.stage_vae_weights("4dof", seed=0), dev, engine=engine)
+    cnn = ops.Cnn4dof(synth.cnn4dof_weights(seed=0), dev)
+    pk = peaks()
+
+    # threshold calibration, as 04_vae_thresholding.py: P99 of a 2,010-window normal set (device percentile)
+    cal_series = torch.from_numpy(synth_problem(2010, seed=7)[1]).to(dev)
+    cal_src = ops.WindowSource(cal_series, T, stride=1, mean=mean, std=std, nan_to_zero=True)
+    torch.manual_seed(42)
+    cal_scores = vae.score(cal_src, torch.randn((2010, Z), device=dev))["score"]
+    thr = float(ops.percentile(cal_scores, 99.0).item()) if a.workload == "4dof_hybrid" else float("inf")
+    hyb = Hybrid4dof(vae, cnn, thr)
+
+    series_pinned = torch.from_numpy(series_h).pin_memory()
+    series_d = series_pinned.to(dev, non_blocking=True)
+    eps1 = torch.randn((N, Z), device=dev)
+    max_flag = max(4096, int(0.05 * N))
+    eps2 = torch.randn((max_flag, Z), device=dev)
+    src = ops.WindowSource(series_d, T, stride=1, mean=mean, std=std, nan_to_zero=True)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)         # > 126 MB L2
+
+    kern_ev = []
+
+    def step(timed: bool):
+        """Device-resident step; the first (dominant) kernel is bracketed by its own CUDA events."""
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = vae.score(src, eps1, n=N)
+            e1.record()
+            kern_ev.append((e0, e1))
+        else:
+            out = vae.score(src, eps1, n=N)
+        score = out["score"]
+        flag, idx, count = ops.compact(score, thr)
+        launches = 2
+        if a.workload == "4dof_hybrid":
+            second = vae.score(src, eps2, n=max_flag, idx=idx, n_dev=count, want_score=False, want_cnn_in=True, out=step.buf)
+            cnn.forward(second["cnn_in"], n=max_flag, n_dev=count, want_labels=True)
+            launches += 3
+        return launches, count
+
+    step.buf = {}
+    launches_per_step = 0
+    for _ in range(a.warmup):
+        launches_per_step, count = step(False)
+    torch.cuda.synchronize()
+    n_flag = int(count.item())
+    if n_flag > max_flag:
+        raise RuntimeError(f"flagged {n_flag} > buffer {max_flag}")
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = []
+    for _ in range(a.steps):
+        flush.zero_()                                                      # L2 flush between timed iterations
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        step(True)
+        s1.record()
+        ev.append((s0, s1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    step_ms = [x.elapsed_time(y) for x, y in ev]
+    total_ms = max_over_ranks(sum(step_ms), dev)
+    kern_ms = sum(x.elapsed_time(y) for x, y in kern_ev) / len(kern_ev)
+    windows_total = sum_over_ranks(float(N * a.steps), dev)
+    value = windows_total / (total_ms / 1e3)
+
+    # ---- end to end through the public API with host buffers ----
+    e2e = None
+    if not a.no_e2e:
+        host_score = torch.empty((N,), dtype=torch.float32).pin_memory()
+        host_pred = torch.empty((N,), dtype=torch.int64).pin_memory()
+        host_p = torch.empty((N,), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            sd_ = series_pinned.to(dev, non_blocking=True)                 # H2D of this step's input
+            src_ = ops.WindowSource(sd_, T, stride=1, mean=mean, std=std, nan_to_zero=True)
+            e1_ = torch.randn((N, Z), device=dev)                          # the reference draws eps on the device too
+            if a.workload == "4dof_hybrid":
+                e2_ = torch.randn((max_flag, Z), device=dev)
+                res = hyb.run(src_, e1_, e2_, n=N)                         # sync_count=True: 4-byte D2H like np.where
+                y_pred, p_full = Hybrid4dof.scatter(res, N)
+                host_pred.copy_(y_pred, non_blocking=True)
+                host_p.copy_(p_full, non_blocking=True)
+            else:
+                res = dict(score=vae.score(src_, e1_, n=N)["score"])
+            host_score.copy_(res["score"], non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+        d2h = N * 4 + (N * 8 + N * 4 + 4 if a.workload == "4dof_hybrid" else 0)
+        e2e = {"value": windows_total / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": int(series_pinned.numel() * 4),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / a.steps,
+               "api": "shmfast.pipeline.Hybrid4dof.run + scatter (host pinned series in, scores/labels/p_struct out)"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        r = cpu_port_run(min(a.cpu_sample, N), 1, 1, thr, a.workload)
+        cpu_baseline = {"value": r["value"], "unit": "windows/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        eng_name = {ops.ENGINE_FP32: "fp32", ops.ENGINE_TC_BF16X3: "tc_bf16x3"}[vae.engine]
+        flops = FLOP_PER_WINDOW["4dof"] * N
+        achieved = flops / (kern_ms / 1e3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if vae.engine == ops.ENGINE_FP32 else "bf16x3->f32",
+            "data": "synthetic",
+            "config": {"workload": a.workload, "windows_per_gpu": N, "T": T, "D": D, "H": s["H"], "Z": Z, "L": s["L"],
+                       "engine": eng_name, "threshold": "P99 of 2010 calibration windows" if a.workload == "4dof_hybrid" else None,
+                       "flagged_per_gpu": n_flag, "input": "raw series, stride 1, gather+normalise fused into the scorer",
+                       "l2": "flushed between timed steps (512 MiB memset)", "parallelism": f"window-range shards x{world}, no collective"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
+            "roofline": {"bound": "tensor", "kernel": "vae_score (fused LSTM-VAE scorer, first pass)", "achieved": achieved,
+                         "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"], "traffic": None,
+                         "peak_source": pk["source"] + " bf16 dense, sustained", "kernel_ms": kern_ms,
+                         "algorithmic_flop_per_window": FLOP_PER_WINDOW["4dof"], "engine": eng_name},
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_shmfast(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+// Threshold + routing: flag = score > thr (strict, fp32) and the ascending list of flagged window
+// indices -- `anom_mask = mse_all > thr; idx = np.where(anom_mask)[0]`
+// (4DOF/Scripts/06_test_full_pipeline.py:350-351, openLAB 10_test_hybrid_pipeline.py:367).
+//
+// Single pass, HBM-bound (4 B read, 1 B flag + 4 B per flagged window written): tiles are claimed in
+// order through an atomic ticket, each CTA ballots its flags, publishes its tile aggregate and
+// resolves its exclusive prefix with a warp-wide decoupled look-back, so the scores are read exactly
+// once and the output order equals np.where's.
+#include "common.cuh"
+
+namespace shm {
+
+constexpr int CP_THREADS = 256;
+constexpr int CP_ITEMS = 8;
+constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
+
+constexpr unsigned long long ST_AGG = 1ull << 62;
+constexpr unsigned long long ST_INC = 2ull << 62;
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(CP_THREADS)
+compact_kernel(const float* __restrict__ score, float thr, long long N, unsigned char* __restrict__ flag,
+               int* __restrict__ idx, int* __restrict__ count, int* ticket, unsigned long long* status, int n_tiles,
+               int vec_ok) {
+    __shared__ int s_tile;
+    __shared__ int s_warp[CP_THREADS / 32];
+    __shared__ int s_excl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= n_tiles) return;
+    const long long base = (long long)tile * CP_TILE + (long long)tid * CP_ITEMS;
+
+    float v[CP_ITEMS];
+    if (vec_ok && base + CP_ITEMS <= N) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(score + base));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(score + base) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < CP_ITEMS; ++i) v[i] = (base + i < N) ? score[base + i] : -INFINITY;
+    }
+    unsigned bits = 0;
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS; ++i) bits |= (v[i] > thr && base + i < N) ? (1u << i) : 0u;   // NaN > thr is false, as NumPy
+    const int cnt = __popc(bits);
+
+    if (flag) {
+        if (vec_ok && base + CP_ITEMS <= N) {
+            unsigned long long packed = 0;
+#pragma unroll
+            for (int i = 0; i < CP_ITEMS; ++i) packed |= (unsigned long long)((bits >> i) & 1u) << (8 * i);
+            *reinterpret_cast<unsigned long long*>(flag + base) = packed;
+        } else {
+            for (int i = 0; i < CP_ITEMS; ++i) if (base + i < N) flag[base + i] = (bits >> i) & 1u;
+        }
+    }
+
+    // block-wide exclusive scan of per-thread counts
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int warp_off = 0, agg = 0;
+#pragma unroll
+    for (int w = 0; w < CP_THREADS / 32; ++w) {
+        const int c = s_warp[w];
+        if (w < warp) warp_off += c;
+        agg += c;
+    }
+
+    // decoupled look-back (warp 0)
+    if (warp == 0) {
+        if (lane == 0) st_status(status + tile, (tile == 0 ? ST_INC : ST_AGG) | (unsigned)agg);
+        int excl = 0;
+        int look = tile - 1;
+        while (look >= 0) {
+            const int t = look - lane;
+            unsigned long long st = (t >= 0) ? ld_status(status + t) : ST_INC;
+            while (__any_sync(0xffffffffu, (st >> 62) == 0)) st = (t >= 0) ? ld_status(status + t) : ST_INC;
+            const unsigned inc_mask = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+            const int val = (int)(st & 0xffffffffu);
+            if (inc_mask) {
+                const int first = __ffs(inc_mask) - 1;           // nearest predecessor with an inclusive prefix
+                int part = (lane <= first) ? val : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                excl += part;
+                break;
+            }
+            int part = val;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            excl += part;
+            look -= 32;
+        }
+        if (lane == 0) {
+            if (tile != 0) st_status(status + tile, ST_INC | (unsigned)(excl + agg));
+            s_excl = excl;
+            if (tile == n_tiles - 1) *count = excl + agg;
+        }
+    }
+    __syncthreads();
+    int pos = s_excl + warp_off + (incl - cnt);
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS; ++i)
+        if ((bits >> i) & 1u) idx[pos++] = (int)(base + i);
+}
+
+}  // namespace shm
+
+extern "C" int64_t shm_compact_workspace_bytes(int64_t N) {
+    if (N < 0) return 0;
+    const int64_t tiles = (N + shm::CP_TILE - 1) / shm::CP_TILE;
+    return 16 + 8 * (tiles > 0 ? tiles : 1);
+}
+
+extern "C" int shm_compact(const float* score, float thr, int64_t N, uint8_t* flag, int32_t* idx, int32_t* count,
+                           void* workspace, void* stream) {
+    using namespace shm;
+    if (N < 0 || N > 0x7fffffffLL || !count || !workspace || (N > 0 && (!score || !idx))) return SHM_ERR_ARG;
+    int dev = 0;
+    SHM_CUDA(cudaGetDevice(&dev));
+    int rc = check_device(dev);
+    if (rc != SHM_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (N == 0) {
+        SHM_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
+        return SHM_OK;
+    }
+    const int n_tiles = (int)((N + CP_TILE - 1) / CP_TILE);
+    SHM_CUDA(cudaMemsetAsync(workspace, 0, (size_t)shm_compact_workspace_bytes(N), st));
+    int* ticket = static_cast<int*>(workspace);
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + 16);
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(score) & 15) == 0) && ((reinterpret_cast<uintptr_t>(flag) & 7) == 0);
+    compact_kernel<<<n_tiles, CP_THREADS, 0, st>>>(score, thr, N, flag, idx, count, ticket, status, n_tiles, vec_ok);
+    SHM_LAUNCH_CHECK();
+    return SHM_OK;
+}

@@ -1,0 +1,26 @@
+// Tensor-core engine (SHM_ENGINE_TC_BF16X3) of the fused LSTM-VAE scorer: interface.
+// Implementation: vae_tc.cu (tcgen05.mma, 3-pass bf16 hi/lo split, fp32 accumulation in TMEM).
+#pragma once
+#include "vae_fp32.cuh"
+
+namespace shm {
+
+struct VaeTcRaw {
+    const float *enc_wih[SHM_MAX_L], *enc_whh[SHM_MAX_L], *enc_bih[SHM_MAX_L], *enc_bhh[SHM_MAX_L];
+    const float *dec_wih[SHM_MAX_L], *dec_whh[SHM_MAX_L], *dec_bih[SHM_MAX_L], *dec_bhh[SHM_MAX_L];
+};
+
+struct VaeTc {
+    void* wpack;       // bf16 hi/lo weight tiles in the UMMA smem layout
+    float* bias;       // packed biases
+    void* scratch;     // inter-layer activation stream
+    size_t wpack_bytes, scratch_bytes;
+};
+
+bool vae_tc_supported(const shm_vae_cfg& cfg);
+int vae_tc_alloc(VaeTc* tc, const shm_vae_cfg& cfg);
+int vae_tc_pack(VaeTc* tc, const shm_vae_cfg& cfg, const VaeTcRaw& raw, cudaStream_t st);
+void vae_tc_free(VaeTc* tc);
+int vae_tc_score(VaeTc* tc, const VaeDev& P, const WinSrc& src, const VaeIO& io, cudaStream_t st);
+
+}  // namespace shm

@@ -1,0 +1,413 @@
+"""Host-side operators over libshmfast's C ABI.  torch is used only for device memory and streams.
+
+Every function takes CUDA tensors and raises on CPU tensors: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ENGINE_AUTO, ENGINE_FP32, ENGINE_TC_BF16X3, ShmfastError, check  # noqa: F401
+
+SHM_MAX_D = _lib.SHM_MAX_D
+
+
+def _need_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ShmfastError(f"{name} must be a CUDA tensor: libshmfast has no CPU fallback")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    _need_cuda(t, name)
+    if t.dtype != torch.float32:
+        raise ShmfastError(f"{name} must be float32")
+    return t.contiguous()
+
+
+class WindowSource:
+    """Describes how windows are read (shm_window_src): a series [rows, d_all] with (T, stride), or
+    materialised windows [N, T, D_all]; optional channel selection and the reference's normalisation
+    (4DOF normalize_windows, 06_test_full_pipeline.py:124-126; openLAB standardize,
+    10_test_hybrid_pipeline.py:233-237).  `std` must already carry the stage's zero-guard."""
+
+    def __init__(self, data: torch.Tensor, T: int, stride: Optional[int] = None, chan: Optional[Sequence[int]] = None,
+                 mean=None, std=None, clip: float = 0.0, nan_to_zero: bool = False):
+        data = _f32c(data, "window data")
+        self.data = data
+        if data.dim() == 2:                      # series
+            if stride is None or stride <= 0:
+                raise ShmfastError("a series source needs a positive stride")
+            rows, d_all = data.shape
+            self.n_windows = 0 if rows < T else (rows - T) // stride + 1
+            win_stride, row_stride = stride * d_all, d_all
+        elif data.dim() == 3:                    # materialised windows
+            if data.shape[1] != T:
+                raise ShmfastError(f"windows have T={data.shape[1]}, expected {T}")
+            self.n_windows, _, d_all = data.shape
+            win_stride, row_stride = T * d_all, d_all
+        else:
+            raise ShmfastError("window data must be [rows, D] or [N, T, D]")
+        chan = list(range(d_all)) if chan is None else [int(c) for c in chan]
+        if not 1 <= len(chan) <= SHM_MAX_D or any(c < 0 or c >= d_all for c in chan):
+            raise ShmfastError("bad channel selection")
+        self.T, self.D = int(T), len(chan)
+        s = _lib.WindowSrc()
+        s.base = data.data_ptr()
+        s.win_stride, s.row_stride, s.T, s.D = win_stride, row_stride, self.T, self.D
+        for i, c in enumerate(chan):
+            s.chan[i] = c
+        s.normalize = 0
+        if mean is not None or std is not None:
+            m = np.zeros(self.D, np.float32) if mean is None else np.asarray(mean, dtype=np.float32).reshape(-1)
+            sd = np.ones(self.D, np.float32) if std is None else np.asarray(std, dtype=np.float32).reshape(-1)
+            if m.size != self.D or sd.size != self.D:
+                raise ShmfastError("mean/std must have one entry per selected channel")
+            s.normalize = 1
+            for i in range(self.D):
+                s.mean[i] = float(m[i])
+                s.std[i] = float(sd[i])
+        s.clip = float(clip)
+        s.nan_to_zero = 1 if nan_to_zero else 0
+        self.struct = s
+
+
+def window_normalize(src: WindowSource, idx: Optional[torch.Tensor] = None, n: Optional[int] = None,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Materialise [n, T, D] fp32 windows (make_windows + normalize_windows of the reference)."""
+    lib = _lib.load()
+    if idx is not None:
+        _need_cuda(idx, "idx")
+        if idx.dtype != torch.int32:
+            raise ShmfastError("idx must be int32")
+        n = idx.numel() if n is None else n
+    n = src.n_windows if n is None else int(n)
+    if out is None:
+        out = torch.empty((n, src.T, src.D), dtype=torch.float32, device=src.data.device)
+    with torch.cuda.device(src.data.device):
+        check(lib.shm_window_normalize(C.byref(src.struct), _ptr(idx), n, _ptr(out), _stream()), "shm_window_normalize")
+    return out
+
+
+VAE_KEYS_PER_LAYER = ("weight_ih", "weight_hh", "bias_ih", "bias_hh")
+
+
+class VaeScorer:
+    """Handle around shm_vae: repacked weights + fused forward/score kernel."""
+
+    def __init__(self, state: dict, device: torch.device, engine: int = ENGINE_AUTO, ln_eps: float = 1e-5):
+        lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ShmfastError("VaeScorer needs a CUDA device: libshmfast has no CPU fallback")
+        w_ih0 = state["encoder_lstm.weight_ih_l0"]
+        self.H = w_ih0.shape[0] // 4
+        self.D = w_ih0.shape[1]
+        self.Z = state["fc_mu.weight"].shape[0]
+        self.L = sum(1 for k in state if k.startswith("encoder_lstm.weight_ih_l"))
+        self.has_ln = "layer_norm.weight" in state
+        cfg = _lib.VaeCfg(self.D, self.H, self.Z, self.L, 1 if self.has_ln else 0, ln_eps, engine)
+        self._keep = None
+        w = self._weights_struct(state)
+        h = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        check(lib.shm_vae_create(C.byref(h), C.byref(cfg), C.byref(w), dev_index), "shm_vae_create")
+        self._h = h
+        self._lib = lib
+        self.engine = lib.shm_vae_engine(h)
+
+    def _weights_struct(self, state: dict) -> _lib.VaeWeights:
+        keep = []
+
+        def p(key):
+            t = state[key]
+            if isinstance(t, np.ndarray):
+                t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32))
+            t = t.detach().to(dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        w = _lib.VaeWeights()
+        for l in range(self.L):
+            w.enc_w_ih[l] = p(f"encoder_lstm.weight_ih_l{l}"); w.enc_w_hh[l] = p(f"encoder_lstm.weight_hh_l{l}")
+            w.enc_b_ih[l] = p(f"encoder_lstm.bias_ih_l{l}"); w.enc_b_hh[l] = p(f"encoder_lstm.bias_hh_l{l}")
+            w.dec_w_ih[l] = p(f"decoder_lstm.weight_ih_l{l}"); w.dec_w_hh[l] = p(f"decoder_lstm.weight_hh_l{l}")
+            w.dec_b_ih[l] = p(f"decoder_lstm.bias_ih_l{l}"); w.dec_b_hh[l] = p(f"decoder_lstm.bias_hh_l{l}")
+        if self.has_ln:
+            w.ln_w = p("layer_norm.weight"); w.ln_b = p("layer_norm.bias")
+        w.fc_mu_w = p("fc_mu.weight"); w.fc_mu_b = p("fc_mu.bias")
+        w.fc_lv_w = p("fc_logvar.weight"); w.fc_lv_b = p("fc_logvar.bias")
+        w.l2h_w = p("fc_latent_to_hidden.weight"); w.l2h_b = p("fc_latent_to_hidden.bias")
+        w.out_w = p("output_layer.weight"); w.out_b = p("output_layer.bias")
+        self._keep = keep          # keep sources alive until the (stream-ordered) copies are done
+        return w
+
+    def update_weights(self, state: dict) -> None:
+        w = self._weights_struct(state)
+        with torch.cuda.device(self.device):
+            check(self._lib.shm_vae_update_weights(self._h, C.byref(w), _stream()), "shm_vae_update_weights")
+            if any(not t.is_cuda for t in self._keep):
+                torch.cuda.current_stream().synchronize()
+
+    def score(self, src: WindowSource, eps: Optional[torch.Tensor], n: Optional[int] = None,
+              idx: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None, want_score: bool = True,
+              want_latent: bool = False, want_recon: bool = False, want_cnn_in: bool = False, out: Optional[dict] = None):
+        """Fused forward.  Returns dict(score, mu, logvar, recon, cnn_in) with the requested tensors."""
+        if src.D != self.D:
+            raise ShmfastError(f"window source has D={src.D}, model expects {self.D}")
+        if idx is not None:
+            _need_cuda(idx, "idx")
+            if idx.dtype != torch.int32:
+                raise ShmfastError("idx must be int32")
+            n = idx.numel() if n is None else n
+        n = src.n_windows if n is None else int(n)
+        dev = src.data.device
+        if eps is not None:
+            eps = _f32c(eps, "eps")
+            if eps.numel() < n * self.Z:
+                raise ShmfastError("eps must hold [n, Z] values")
+        out = {} if out is None else out
+
+        def buf(name, want, shape):
+            if not want:
+                return None
+            t = out.get(name)
+            if t is None:
+                t = torch.empty(shape, dtype=torch.float32, device=dev)
+                out[name] = t
+            return t
+
+        score = buf("score", want_score, (n,))
+        mu = buf("mu", want_latent, (n, self.Z))
+        lv = buf("logvar", want_latent, (n, self.Z))
+        recon = buf("recon", want_recon, (n, src.T, self.D))
+        cnn_in = buf("cnn_in", want_cnn_in, (n, 2, src.T, self.D))
+        with torch.cuda.device(dev):
+            check(self._lib.shm_vae_score(self._h, C.byref(src.struct), _ptr(idx), _ptr(n_dev), _ptr(eps), n, _ptr(score),
+                                          _ptr(mu), _ptr(lv), _ptr(recon), _ptr(cnn_in), _stream()), "shm_vae_score")
+        return out
+
+    def decode(self, z: torch.Tensor, T: int) -> torch.Tensor:
+        """TemporalVAE.decode (temporal_vae.py:65-70): z [n,Z] -> recon [n,T,D]."""
+        z = _f32c(z, "z")
+        if z.dim() != 2 or z.shape[1] != self.Z:
+            raise ShmfastError(f"z must be [n, {self.Z}]")
+        recon = torch.empty((z.shape[0], int(T), self.D), dtype=torch.float32, device=z.device)
+        with torch.cuda.device(z.device):
+            check(self._lib.shm_vae_decode(self._h, _ptr(z), z.shape[0], int(T), _ptr(recon), _stream()), "shm_vae_decode")
+        return recon
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.shm_vae_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def compact(score: torch.Tensor, thr: float, want_flag: bool = True):
+    """flag = score > thr (strict fp32), idx = np.where(flag)[0] ascending, count (device int32[1]).
+    06_test_full_pipeline.py:350-351."""
+    lib = _lib.load()
+    score = _f32c(score, "score")
+    N = score.numel()
+    dev = score.device
+    flag = torch.empty((N,), dtype=torch.uint8, device=dev) if want_flag else None
+    idx = torch.empty((max(N, 1),), dtype=torch.int32, device=dev)
+    count = torch.empty((1,), dtype=torch.int32, device=dev)
+    ws = torch.empty((int(lib.shm_compact_workspace_bytes(N)),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.shm_compact(_ptr(score), float(np.float32(thr)), N, _ptr(flag), _ptr(idx), _ptr(count), _ptr(ws), _stream()),
+              "shm_compact")
+    return flag, idx, count
+
+
+class Cnn4dof:
+    """Handle around shm_cnn4dof (4DOF/Scripts/Models/cnn_model.py, eval mode)."""
+
+    def __init__(self, state: dict, device: torch.device, bn_eps: float = 1e-5):
+        self._lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ShmfastError("Cnn4dof needs a CUDA device: libshmfast has no CPU fallback")
+        self.bn_eps = bn_eps
+        w = self._weights_struct(state)
+        h = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        check(self._lib.shm_cnn4dof_create(C.byref(h), C.byref(w), dev_index), "shm_cnn4dof_create")
+        self._h = h
+
+    def _weights_struct(self, state):
+        keep = []
+
+        def p(key):
+            t = state[key]
+            if isinstance(t, np.ndarray):
+                t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32))
+            t = t.detach().to(dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        w = _lib.Cnn4dofWeights()
+        for b, blk in enumerate(("conv1", "conv2")):
+            w.conv_w[b] = p(f"{blk}.0.weight"); w.conv_b[b] = p(f"{blk}.0.bias")
+            w.bn_w[b] = p(f"{blk}.1.weight"); w.bn_b[b] = p(f"{blk}.1.bias")
+            w.bn_mean[b] = p(f"{blk}.1.running_mean"); w.bn_var[b] = p(f"{blk}.1.running_var")
+        w.fc1_w = p("fc1.0.weight"); w.fc1_b = p("fc1.0.bias"); w.fc2_w = p("fc2.weight"); w.fc2_b = p("fc2.bias")
+        w.bn_eps = self.bn_eps
+        self._keep = keep
+        return w
+
+    def update_weights(self, state: dict) -> None:
+        w = self._weights_struct(state)
+        with torch.cuda.device(self.device):
+            check(self._lib.shm_cnn4dof_update_weights(self._h, C.byref(w), _stream()), "shm_cnn4dof_update_weights")
+            if any(not t.is_cuda for t in self._keep):
+                torch.cuda.current_stream().synchronize()
+
+    def forward(self, x: torch.Tensor, n: Optional[int] = None, n_dev: Optional[torch.Tensor] = None,
+                want_labels: bool = False):
+        x = _f32c(x, "x")
+        if x.dim() != 4 or tuple(x.shape[1:]) != (2, 100, 12):
+            raise ShmfastError(f"4DOF CNN expects [n,2,100,12], got {tuple(x.shape)}")
+        n = x.shape[0] if n is None else int(n)
+        logits = torch.empty((n, 2), dtype=torch.float32, device=x.device)
+        label = torch.empty((n,), dtype=torch.int64, device=x.device) if want_labels else None
+        p_struct = torch.empty((n,), dtype=torch.float32, device=x.device) if want_labels else None
+        with torch.cuda.device(x.device):
+            check(self._lib.shm_cnn4dof_forward(self._h, _ptr(x), _ptr(n_dev), n, _ptr(logits), _ptr(label), _ptr(p_struct),
+                                                _stream()), "shm_cnn4dof_forward")
+        return (logits, label, p_struct) if want_labels else logits
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.shm_cnn4dof_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CnnOpenLab:
+    """Handle around shm_cnnol (openLAB Codes/Models/cnn_model.py, eval mode)."""
+
+    BLOCKS = (0, 2, 4, 6)
+
+    def __init__(self, state: dict, device: torch.device, gn_eps: float = 1e-5):
+        self._lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ShmfastError("CnnOpenLab needs a CUDA device: libshmfast has no CPU fallback")
+        self.gn_eps = gn_eps
+        w = self._weights_struct(state)
+        h = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        check(self._lib.shm_cnnol_create(C.byref(h), C.byref(w), dev_index), "shm_cnnol_create")
+        self._h = h
+
+    def _weights_struct(self, state):
+        keep = []
+
+        def p(key):
+            t = state[key]
+            if isinstance(t, np.ndarray):
+                t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32))
+            t = t.detach().to(dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        w = _lib.CnnOlWeights()
+        for b, i in enumerate(self.BLOCKS):
+            w.conv_w[b] = p(f"features.{i}.0.weight"); w.conv_b[b] = p(f"features.{i}.0.bias")
+            w.gn_w[b] = p(f"features.{i}.1.weight"); w.gn_b[b] = p(f"features.{i}.1.bias")
+        w.fc1_w = p("classifier.1.weight"); w.fc1_b = p("classifier.1.bias")
+        w.fc2_w = p("classifier.4.weight"); w.fc2_b = p("classifier.4.bias")
+        w.gn_eps = self.gn_eps
+        self._keep = keep
+        return w
+
+    def update_weights(self, state: dict) -> None:
+        w = self._weights_struct(state)
+        with torch.cuda.device(self.device):
+            check(self._lib.shm_cnnol_update_weights(self._h, C.byref(w), _stream()), "shm_cnnol_update_weights")
+            if any(not t.is_cuda for t in self._keep):
+                torch.cuda.current_stream().synchronize()
+
+    def forward(self, src: WindowSource, n: Optional[int] = None, idx: Optional[torch.Tensor] = None,
+                n_dev: Optional[torch.Tensor] = None, want_prob: bool = False):
+        if src.T != 200 or src.D != 4:
+            raise ShmfastError("openLAB CNN expects windows of T=200, D=4")
+        if idx is not None:
+            _need_cuda(idx, "idx")
+            if idx.dtype != torch.int32:
+                raise ShmfastError("idx must be int32")
+            n = idx.numel() if n is None else n
+        n = src.n_windows if n is None else int(n)
+        dev = src.data.device
+        logits = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        prob = torch.empty((n,), dtype=torch.float64, device=dev) if want_prob else None
+        with torch.cuda.device(dev):
+            check(self._lib.shm_cnnol_forward(self._h, C.byref(src.struct), _ptr(idx), _ptr(n_dev), n, _ptr(logits), _ptr(prob),
+                                              _stream()), "shm_cnnol_forward")
+        return (logits, prob) if want_prob else logits
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.shm_cnnol_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def stitch_segment_rmse(recon: torch.Tensor, full_len: int, stride: int, mean, std, y_true: Optional[torch.Tensor],
+                        segment_len: int, want_series: bool = True):
+    """1_DOF stitch_windows -> destandardize -> segment_rmse (datasets.py:21-22,38-71), fp64."""
+    lib = _lib.load()
+    recon = _f32c(recon, "recon")
+    N, T, F = recon.shape
+    dev = recon.device
+    mean_d = torch.as_tensor(np.asarray(mean, dtype=np.float64), device=dev)
+    std_d = torch.as_tensor(np.asarray(std, dtype=np.float64), device=dev)
+    series = torch.empty((full_len, F), dtype=torch.float64, device=dev) if want_series else None
+    rm = None
+    if y_true is not None:
+        y_true = _f32c(y_true, "y_true")
+        rm = torch.empty(((full_len + segment_len - 1) // segment_len,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.shm_stitch_segment_rmse(_ptr(recon), N, T, F, stride, full_len, _ptr(mean_d), _ptr(std_d), _ptr(y_true),
+                                          segment_len, _ptr(series), _ptr(rm), _stream()), "shm_stitch_segment_rmse")
+    return series, rm
+
+
+def percentile(scores: torch.Tensor, q: float) -> torch.Tensor:
+    """np.percentile(scores, q) (linear interpolation, fp32 arithmetic like NumPy) -> device fp64[1]."""
+    lib = _lib.load()
+    scores = _f32c(scores, "scores")
+    dev = scores.device
+    res = torch.empty((1,), dtype=torch.float64, device=dev)
+    ws = torch.empty((int(lib.shm_percentile_workspace_bytes(scores.numel())),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.shm_percentile(_ptr(scores), scores.numel(), float(q), _ptr(res), _ptr(ws), _stream()), "shm_percentile")
+    return res

@@ -1,0 +1,239 @@
+/*
+ * shmfast.h -- C ABI of libshmfast.so: B200 (sm_100a) hybrid window scoring for structural-health
+ * monitoring.  Drop-in boundary for ONE hot path of Ogunleyemma1/Hybrid-VAE-CNN-for-SHM:
+ * window gather+normalise -> LSTM-VAE gate -> per-window reconstruction MSE -> stored-threshold
+ * compare + ascending compaction -> CNN attribution on the flagged windows.
+ *
+ * The reference has no FFI: its seam is the Python class surface of `Models/` and the inner loops of
+ * its numbered scripts.  Each entry point below cites the reference code it
+ * replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes binding and the
+ * `Models/` shim a maintainer adds.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns every buffer; the library owns only its handles (repacked weights, workspace);
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default);
+ *   - return value: 0 = SHM_OK, negative = error (shm_strerror); never throws, never aborts;
+ *   - there is NO CPU fallback: without a CUDA device of compute capability 10.x every compute
+ *     entry point returns SHM_ERR_DEVICE.
+ */
+#ifndef SHMFAST_H
+#define SHMFAST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHM_MAX_D 16      /* max channels per window fed to the VAE / CNN gather            */
+#define SHM_MAX_L 2       /* max stacked LSTM layers (reference uses 1 and 2)                */
+
+enum {
+    SHM_OK = 0,
+    SHM_ERR_ARG = -1,         /* null pointer / negative size / inconsistent shapes          */
+    SHM_ERR_UNSUPPORTED = -2, /* configuration outside the supported set (see shm_vae_cfg)   */
+    SHM_ERR_CUDA = -3,        /* a CUDA runtime call failed (shm_last_cuda_error)            */
+    SHM_ERR_DEVICE = -4,      /* no CUDA device, or not compute capability 10.x (B200)       */
+    SHM_ERR_NOMEM = -5
+};
+
+const char* shm_strerror(int code);
+const char* shm_last_cuda_error(void);        /* text of the last CUDA failure on this thread */
+int shm_version(void);                        /* 10000*major + 100*minor + patch              */
+int shm_device_check(int device);             /* SHM_OK iff `device` is an sm_100 part        */
+
+/* ---------------------------------------------------------------------------------------------
+ * Window source: how x[n][t][d] is produced.  One description serves both the materialising
+ * gather kernel and the fused scorers (which then never write the windows to HBM):
+ *
+ *     raw  = base[ win(n) * win_stride + t * row_stride + chan[d] ]
+ *     x    = normalize ? (raw - mean[d]) / std[d] : raw          (IEEE fp32 divide, as NumPy)
+ *     x    = clip > 0  ? min(max(x, -clip), clip) : x            (NaN passes through, as np.clip)
+ *     x    = nan_to_zero && !isfinite(x) ? 0 : x                 (np.nan_to_num(nan=0,posinf=0,neginf=0))
+ *
+ * with win(n) = idx ? idx[n] : n.  Replaces make_windows + normalize_windows
+ * (4DOF/Scripts/06_test_full_pipeline.py:106-126, copies in 03/04/05), windowize_2d + standardize +
+ * channel select (openLAB feature_utils.py:130-152, 10_test_hybrid_pipeline.py:233-237,351) and
+ * standardize + make_windows (1_DOF/Scripts/datasets.py:17-35).  The per-stage std guards
+ * (std==0 -> 1e-6; sd<1e-12 -> 1; sd<1e-8 -> 1) are applied by the caller to `std` beforehand,
+ * exactly where the reference applies them (load_stats / fit_mean_std).
+ *
+ *   series [rows, d_all], stride s : win_stride = s*d_all, row_stride = d_all, chan = column ids
+ *   windows [N, T, D_all]          : win_stride = T*D_all, row_stride = D_all
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* base;
+    int64_t win_stride;
+    int64_t row_stride;
+    int32_t T;
+    int32_t D;
+    int32_t chan[SHM_MAX_D];
+    int32_t normalize;
+    int32_t nan_to_zero;
+    float clip;                 /* <= 0 : no clipping */
+    float mean[SHM_MAX_D];
+    float std[SHM_MAX_D];
+} shm_window_src;
+
+/* Materialise out[n, t, d] (C-contiguous [N,T,D] fp32) for n in [0,N).  `idx` (optional, device,
+ * int32[N]) selects source windows (np fancy indexing Z[sel], 06_test_full_pipeline.py:362). */
+int shm_window_normalize(const shm_window_src* src_host, const int32_t* idx, int64_t N, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LSTM-VAE (TemporalVAE / VAE): 4DOF/Scripts/Models/temporal_vae.py:14-77,
+ * 1_DOF/Scripts/Models/temporal_vae.py:8-58, openLAB Codes/Models/temporal_vae_model.py:4-66.
+ * Supported: H in {32, 64, 128}, 1 <= L <= SHM_MAX_L, 1 <= D <= SHM_MAX_D, 1 <= Z <= 16.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t D, H, Z, L;
+    int32_t has_ln;             /* LayerNorm on h_n[-1] (4DOF, openLAB) or not (1_DOF)         */
+    float ln_eps;               /* 1e-5                                                         */
+    int32_t engine;             /* SHM_ENGINE_*                                                 */
+} shm_vae_cfg;
+
+enum {
+    SHM_ENGINE_AUTO = 0,        /* fastest engine that meets the 1e-4 score tolerance          */
+    SHM_ENGINE_FP32 = 1,        /* fp32 FMA recurrence (any supported shape)                   */
+    SHM_ENGINE_TC_BF16X3 = 2    /* tcgen05 tensor cores, 3-pass bf16 hi/lo split, fp32 accum   */
+};
+
+/* state_dict tensors, reference key names in comments; all fp32, row-major, device or host
+ * pointers (copied + repacked at create/update; not referenced afterwards). */
+typedef struct {
+    const float* enc_w_ih[SHM_MAX_L];   /* encoder_lstm.weight_ih_l{k} [4H, D or H], gate rows i,f,g,o */
+    const float* enc_w_hh[SHM_MAX_L];   /* encoder_lstm.weight_hh_l{k} [4H, H]  */
+    const float* enc_b_ih[SHM_MAX_L];   /* encoder_lstm.bias_ih_l{k}   [4H]     */
+    const float* enc_b_hh[SHM_MAX_L];   /* encoder_lstm.bias_hh_l{k}   [4H]     */
+    const float* ln_w;                  /* layer_norm.weight [H] (NULL if !has_ln) */
+    const float* ln_b;                  /* layer_norm.bias   [H] */
+    const float* fc_mu_w;               /* fc_mu.weight [Z,H] */
+    const float* fc_mu_b;               /* fc_mu.bias   [Z]   */
+    const float* fc_lv_w;               /* fc_logvar.weight [Z,H] */
+    const float* fc_lv_b;               /* fc_logvar.bias   [Z]   */
+    const float* l2h_w;                 /* fc_latent_to_hidden.weight [H,Z] */
+    const float* l2h_b;                 /* fc_latent_to_hidden.bias   [H]   */
+    const float* dec_w_ih[SHM_MAX_L];   /* decoder_lstm.weight_ih_l{k} [4H, H] */
+    const float* dec_w_hh[SHM_MAX_L];   /* decoder_lstm.weight_hh_l{k} [4H, H] */
+    const float* dec_b_ih[SHM_MAX_L];   /* decoder_lstm.bias_ih_l{k}   [4H]    */
+    const float* dec_b_hh[SHM_MAX_L];   /* decoder_lstm.bias_hh_l{k}   [4H]    */
+    const float* out_w;                 /* output_layer.weight [D,H] */
+    const float* out_b;                 /* output_layer.bias   [D]   */
+} shm_vae_weights;
+
+typedef struct shm_vae shm_vae;
+
+int shm_vae_create(shm_vae** out, const shm_vae_cfg* cfg_host, const shm_vae_weights* w_host, int device);
+/* refresh after load_state_dict()/optimizer.step(); asynchronous on `stream` */
+int shm_vae_update_weights(shm_vae* h, const shm_vae_weights* w_host, void* stream);
+int shm_vae_destroy(shm_vae* h);
+int shm_vae_engine(const shm_vae* h);    /* the engine actually selected */
+
+/* Fused forward + score for n windows: encode -> z = mu + eps*exp(0.5*logvar) -> decode ->
+ * score[n] = mean_{t,d} (x - xhat)^2.  Replaces TemporalVAE.forward (temporal_vae.py:72-77) and the
+ * scoring loops full_mse_scores_batched (4DOF/Scripts/04_vae_thresholding.py:113-124),
+ * 06_test_full_pipeline.py:338-344, recon_mse_per_window (openLAB 10_test_hybrid_pipeline.py:240-251).
+ *
+ *   src_host : window source (base may point at a series or at materialised windows)
+ *   idx      : optional int32[n] source-window list (second pass on flagged windows, 06:358-366)
+ *   n_dev    : optional device int32; if non-NULL the effective count is min(*n_dev, n) so the
+ *              flagged-subset pass needs no host round trip
+ *   eps      : [n,Z] fp32 host-drawn noise (the reference's torch.randn_like, temporal_vae.py:62);
+ *              NULL = deterministic z = mu (extra mode, not reference behaviour)
+ *   score, mu, logvar, recon, cnn_in : optional outputs ([n], [n,Z], [n,Z], [n,T,D], [n,2,T,D]);
+ *              cnn_in is stack([x, (x-xhat)^2], dim=1) of 06_test_full_pipeline.py:364-365 /
+ *              05_train_cnn.py:136-138.  The reconstruction stays on chip unless recon/cnn_in is given.
+ */
+int shm_vae_score(shm_vae* h, const shm_window_src* src_host, const int32_t* idx, const int32_t* n_dev,
+                  const float* eps, int64_t n, float* score, float* mu, float* logvar, float* recon,
+                  float* cnn_in, void* stream);
+
+/* TemporalVAE.decode(z, seq_len) (temporal_vae.py:65-70): z [n,Z] -> recon [n,T,D]. */
+int shm_vae_decode(shm_vae* h, const float* z, int64_t n, int32_t T, float* recon, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Threshold + routing: mask = score > thr (strict, fp32), idx = np.where(mask)[0] ascending
+ * (06_test_full_pipeline.py:350-351, 10_test_hybrid_pipeline.py:367).
+ *   flag  : optional uint8[N];  idx : int32[N] (first *count entries valid);  count : device int32
+ *   workspace : device scratch of shm_compact_workspace_bytes(N) bytes
+ * ------------------------------------------------------------------------------------------- */
+int64_t shm_compact_workspace_bytes(int64_t N);
+int shm_compact(const float* score, float thr, int64_t N, uint8_t* flag, int32_t* idx, int32_t* count,
+                void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 4DOF CNN (sensor-fault vs structural-fault): 4DOF/Scripts/Models/cnn_model.py:8-57, eval mode
+ * (BatchNorm running stats, Dropout identity).  x [n,2,100,12] -> logits [n,2];
+ * optional label = argmax+1 (int64, tie -> 1) and p_struct = softmax[:,1]
+ * (06_test_full_pipeline.py:366-372).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* conv_w[2];     /* conv{1,2}.0.weight [16,2,3,3], [32,16,3,3] */
+    const float* conv_b[2];     /* conv{1,2}.0.bias */
+    const float* bn_w[2];       /* conv{1,2}.1.weight */
+    const float* bn_b[2];       /* conv{1,2}.1.bias */
+    const float* bn_mean[2];    /* conv{1,2}.1.running_mean */
+    const float* bn_var[2];     /* conv{1,2}.1.running_var */
+    const float* fc1_w;         /* fc1.0.weight [128,2400] */
+    const float* fc1_b;
+    const float* fc2_w;         /* fc2.weight [2,128] */
+    const float* fc2_b;
+    float bn_eps;               /* 1e-5 */
+} shm_cnn4dof_weights;
+
+typedef struct shm_cnn4dof shm_cnn4dof;
+int shm_cnn4dof_create(shm_cnn4dof** out, const shm_cnn4dof_weights* w_host, int device);
+int shm_cnn4dof_update_weights(shm_cnn4dof* h, const shm_cnn4dof_weights* w_host, void* stream);
+int shm_cnn4dof_destroy(shm_cnn4dof* h);
+int shm_cnn4dof_forward(shm_cnn4dof* h, const float* x, const int32_t* n_dev, int64_t n, float* logits,
+                        int64_t* label, float* p_struct, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * openLAB CNN: 20250506_openLAB_tests/Codes/Models/cnn_model.py:8-57 (Conv+GroupNorm(8)+SiLU x4,
+ * MaxPool(2,1) x3, GAP, 256->128 SiLU ->2), eval mode.  The input is described by a window source
+ * over X_raw (T=200, D=4) so the flagged-window gather + standardise (clip 10, NaN->0) of
+ * stage2_predict_cnn (10_test_hybrid_pipeline.py:272-278) is fused into the first convolution.
+ * prob = softmax[:,1] widened to fp64 for the `>= thr` decision (:294-301).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* conv_w[4];     /* features.{0,2,4,6}.0.weight [32,1,7,3],[64,32,5,3],[128,64,5,3],[256,128,3,3] */
+    const float* conv_b[4];     /* features.{0,2,4,6}.0.bias */
+    const float* gn_w[4];       /* features.{0,2,4,6}.1.weight */
+    const float* gn_b[4];       /* features.{0,2,4,6}.1.bias */
+    const float* fc1_w;         /* classifier.1.weight [128,256] */
+    const float* fc1_b;
+    const float* fc2_w;         /* classifier.4.weight [2,128] */
+    const float* fc2_b;
+    float gn_eps;               /* 1e-5 */
+} shm_cnnol_weights;
+
+typedef struct shm_cnnol shm_cnnol;
+int shm_cnnol_create(shm_cnnol** out, const shm_cnnol_weights* w_host, int device);
+int shm_cnnol_update_weights(shm_cnnol* h, const shm_cnnol_weights* w_host, void* stream);
+int shm_cnnol_destroy(shm_cnnol* h);
+int shm_cnnol_forward(shm_cnnol* h, const shm_window_src* src_host, const int32_t* idx, const int32_t* n_dev,
+                      int64_t n, float* logits, double* prob, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 1_DOF post-processing: overlap-average reconstructed windows back to a series, de-standardise,
+ * RMSE per `segment_len` rows over all channels -- stitch_windows / destandardize / segment_rmse
+ * (1_DOF/Scripts/datasets.py:21-22,38-71; call site 04_test_seen_variants.py:296-311).  fp64 like
+ * the reference.  recon [N,T,F] fp32; y_true [full_len,F] fp32 (physical units); mean/std fp64[F];
+ * series_out optional [full_len,F] fp64; rmse_out [ceil(full_len/segment_len)] fp64.
+ * ------------------------------------------------------------------------------------------- */
+int shm_stitch_segment_rmse(const float* recon, int64_t N, int32_t T, int32_t F, int32_t stride, int64_t full_len,
+                            const double* mean, const double* std, const float* y_true, int32_t segment_len,
+                            double* series_out, double* rmse_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Exact percentile on device with NumPy's default linear interpolation:
+ * np.percentile(scores, q) of 04_vae_thresholding.py:283 / openLAB 05_validate_vae.py:253.
+ * result: device double.  workspace: shm_percentile_workspace_bytes(N).
+ * ------------------------------------------------------------------------------------------- */
+int64_t shm_percentile_workspace_bytes(int64_t N);
+int shm_percentile(const float* scores, int64_t N, double q, double* result, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHMFAST_H */

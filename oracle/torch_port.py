@@ -1,0 +1,131 @@
+"""CPU port of the reference path on torch.nn primitives (TEST / BASELINE INFRASTRUCTURE ONLY).
+
+The reference's arithmetic IS torch.nn (nn.LSTM / Linear / LayerNorm / Conv2d / BatchNorm2d /
+GroupNorm), so the faithful CPU baseline is the same library kernels (MKL /
+oneDNN) driven by a restatement of the reference's module wiring and inner loops.  The reference's
+Python sources cannot travel to the GPU box (/root/reference is absent there), hence a port:
+bench.py's `cpu_baseline` and `--impl reference` legs time THIS on the host cores
+(`cpu_baseline.kind = "port"`).  Checked against the golden vectors in tests/test_oracle_golden.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+class VaePort(nn.Module):
+    """Wiring of TemporalVAE (4DOF/Scripts/Models/temporal_vae.py:14-77; 1_DOF twin without
+    LayerNorm :8-58; openLAB Codes/Models/temporal_vae_model.py:4-66), built from a state_dict."""
+
+    def __init__(self, sd: dict):
+        super().__init__()
+        w = sd["encoder_lstm.weight_ih_l0"]
+        H, D = w.shape[0] // 4, w.shape[1]
+        L = sum(1 for k in sd if k.startswith("encoder_lstm.weight_ih_l"))
+        Z = sd["fc_mu.weight"].shape[0]
+        self.enc = nn.LSTM(D, H, L, batch_first=True)
+        self.dec = nn.LSTM(H, H, L, batch_first=True)
+        self.ln = nn.LayerNorm(H) if "layer_norm.weight" in sd else None
+        self.mu, self.lv = nn.Linear(H, Z), nn.Linear(H, Z)
+        self.l2h, self.out = nn.Linear(Z, H), nn.Linear(H, D)
+        remap = {"encoder_lstm": "enc", "decoder_lstm": "dec", "layer_norm": "ln", "fc_mu": "mu", "fc_logvar": "lv",
+                 "fc_latent_to_hidden": "l2h", "output_layer": "out"}
+        self.load_state_dict({remap[k.split(".")[0]] + "." + k.split(".", 1)[1]: _t(np.asarray(v)) for k, v in sd.items()})
+        self.eval()
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, eps: torch.Tensor | None):
+        _, (h_n, _) = self.enc(x)
+        h = h_n[-1]
+        if self.ln is not None:
+            h = self.ln(h)
+        mu, lv = self.mu(h), self.lv(h)
+        z = mu if eps is None else mu + eps * torch.exp(0.5 * lv)
+        u = torch.tanh(self.l2h(z)).unsqueeze(1).repeat(1, x.size(1), 1)     # temporal_vae.py:67-68
+        y, _ = self.dec(u)
+        return self.out(y), mu, lv
+
+
+@torch.no_grad()
+def vae_scores_batched(vae: VaePort, X: np.ndarray, eps: np.ndarray | None, batch: int) -> np.ndarray:
+    """full_mse_scores_batched (4DOF/Scripts/04_vae_thresholding.py:113-124) /
+    recon_mse_per_window (openLAB 10_test_hybrid_pipeline.py:240-251); eps=None draws randn like the
+    reference does."""
+    out = np.zeros((X.shape[0],), dtype=np.float32)
+    for i in range(0, X.shape[0], batch):
+        xb = torch.tensor(X[i:i + batch], dtype=torch.float32)
+        e = torch.randn((xb.shape[0], vae.mu.out_features)) if eps is None else _t(eps[i:i + batch])
+        xhat, _, _ = vae(xb, e)
+        out[i:i + batch] = ((xb - xhat) ** 2).mean(dim=(1, 2)).numpy().astype(np.float32)
+    return out
+
+
+class Cnn4dofPort(nn.Module):
+    """4DOF/Scripts/Models/cnn_model.py:16-34,45-51."""
+
+    def __init__(self, sd: dict):
+        super().__init__()
+        self.conv1 = nn.Sequential(nn.Conv2d(2, 16, 3, padding=1), nn.BatchNorm2d(16), nn.ReLU(), nn.MaxPool2d(2))
+        self.conv2 = nn.Sequential(nn.Conv2d(16, 32, 3, padding=1), nn.BatchNorm2d(32), nn.ReLU(), nn.MaxPool2d(2))
+        self.fc1 = nn.Sequential(nn.Linear(2400, 128), nn.ReLU())
+        self.fc2 = nn.Linear(128, 2)
+        self.load_state_dict({k: _t(np.asarray(v)) for k, v in sd.items()})
+        self.eval()
+
+    @torch.no_grad()
+    def forward(self, x):
+        return self.fc2(self.fc1(torch.flatten(self.conv2(self.conv1(x)), 1)))
+
+
+class CnnOpenLabPort(nn.Module):
+    """20250506_openLAB_tests/Codes/Models/cnn_model.py:16-43,54-57."""
+
+    def __init__(self, sd: dict):
+        super().__init__()
+
+        def block(ci, co, kt, pt):
+            return nn.Sequential(nn.Conv2d(ci, co, (kt, 3), padding=(pt, 1)), nn.GroupNorm(8, co), nn.SiLU())
+
+        self.features = nn.Sequential(block(1, 32, 7, 3), nn.MaxPool2d((2, 1)), block(32, 64, 5, 2), nn.MaxPool2d((2, 1)),
+                                      block(64, 128, 5, 2), nn.MaxPool2d((2, 1)), block(128, 256, 3, 1), nn.AdaptiveAvgPool2d((1, 1)))
+        self.classifier = nn.Sequential(nn.Flatten(), nn.Linear(256, 128), nn.SiLU(), nn.Identity(), nn.Linear(128, 2))
+        self.load_state_dict({k: _t(np.asarray(v)) for k, v in sd.items()})
+        self.eval()
+
+    @torch.no_grad()
+    def forward(self, x):
+        return self.classifier(self.features(x))
+
+
+@torch.no_grad()
+def hybrid_4dof(vae: VaePort, cnn: Cnn4dofPort, series: np.ndarray, mean, std, thr: float, eps1=None, eps2=None,
+                T: int = 100, stride: int = 1, batch: int = 512) -> dict:
+    """The whole reference hot path for one group of 4DOF windows: make_windows + normalize_windows
+    (06_test_full_pipeline.py:106-126) -> score loop (:338-344) -> threshold (:350-351) -> second VAE
+    pass + residual stack + CNN + labels (:358-372)."""
+    N = 0 if series.shape[0] < T else (series.shape[0] - T) // stride + 1
+    W = np.stack([series[i:i + T] for i in range(0, series.shape[0] - T + 1, stride)], axis=0).astype(np.float32)
+    Z = (W - mean[None, None, :]) / std[None, None, :]
+    Z = np.nan_to_num(Z, nan=0.0, posinf=0.0, neginf=0.0).astype(np.float32)
+    score = vae_scores_batched(vae, Z, eps1, batch)
+    mask = score > thr
+    idx = np.where(mask)[0]
+    y_pred = np.zeros((N,), dtype=np.int64)
+    p_struct = np.zeros((N,), dtype=np.float32)
+    logits_all = np.zeros((idx.size, 2), dtype=np.float32)
+    for j in range(0, idx.size, batch):
+        sel = idx[j:j + batch]
+        zb = torch.tensor(Z[sel], dtype=torch.float32)
+        e = torch.randn((zb.shape[0], vae.mu.out_features)) if eps2 is None else _t(eps2[j:j + batch])
+        xhat, _, _ = vae(zb, e)
+        logits = cnn(torch.stack([zb, (zb - xhat) ** 2], dim=1))
+        logits_all[j:j + batch] = logits.numpy()
+        y_pred[sel] = torch.argmax(logits, dim=1).numpy().astype(np.int64) + 1
+        p_struct[sel] = torch.softmax(logits, dim=1).numpy().astype(np.float32)[:, 1]
+    return dict(score=score, mask=mask, idx=idx, logits=logits_all, y_pred=y_pred, p_struct=p_struct, n=N)

@@ -136,3 +136,27 @@ def test_flag_compact_strict_fp32():
     mask, idx = O.flag_compact(s, 1.2814043760299683)
     assert mask.tolist() == [False, False, True, True, False] or mask.tolist() == [False, False, True, True, False]
     assert idx.tolist() == np.where(mask)[0].tolist()
+
+
+def test_torch_port_matches_goldens(golden_dir):
+    """The torch.nn port timed as the CPU baseline reproduces the reference outputs too."""
+    import torch
+    from oracle import torch_port as TP
+    g = np.load(golden_dir / "synth_vae_4dof_s3.npz")
+    sd = synth.stage_vae_weights("4dof", seed=int(g["seed"]), scale=3.0)
+    X = synth.windows(int(g["N"]), 100, 12, seed=int(g["seed"]), amp=2.5)
+    eps = synth.eps(int(g["N"]), 16, seed=int(g["seed"]))
+    score = TP.vae_scores_batched(TP.VaePort(sd), X, eps, 32)
+    assert _rel(score, g["score"]) < 1e-6
+    g = np.load(golden_dir / "synth_cnnol.npz")
+    x = synth.windows(int(g["N"]), 200, 4, seed=31, amp=1.5)[:, None]
+    logits = TP.CnnOpenLabPort(synth.cnnol_weights(seed=int(g["seed"])))(torch.from_numpy(x)).numpy()
+    assert np.allclose(logits, g["logits"], rtol=1e-5, atol=1e-5)
+    p = golden_dir / "trained_4dof.npz"
+    if p.exists():
+        g = np.load(p)
+        vae_sd = {k[4:]: g[k] for k in g.files if k.startswith("vae.")}
+        cnn_sd = {k[4:]: g[k] for k in g.files if k.startswith("cnn.")}
+        vae, cnn = TP.VaePort(vae_sd), TP.Cnn4dofPort(cnn_sd)
+        score = TP.vae_scores_batched(vae, g["Z"], synth.eps(g["Z"].shape[0], 16, seed=41), 512)
+        assert _rel(score, g["score"]) < 1e-6
