@@ -95,6 +95,8 @@ def window_normalize(src: WindowSource, idx: Optional[torch.Tensor] = None, n: O
     n = src.n_windows if n is None else int(n)
     if out is None:
         out = torch.empty((n, src.T, src.D), dtype=torch.float32, device=src.data.device)
+    if n == 0:
+        return out
     with torch.cuda.device(src.data.device):
         check(lib.shm_window_normalize(C.byref(src.struct), _ptr(idx), n, _ptr(out), _stream()), "shm_window_normalize")
     return out
@@ -193,6 +195,8 @@ class VaeScorer:
         lv = buf("logvar", want_latent, (n, self.Z))
         recon = buf("recon", want_recon, (n, src.T, self.D))
         cnn_in = buf("cnn_in", want_cnn_in, (n, 2, src.T, self.D))
+        if n == 0:
+            return out
         with torch.cuda.device(dev):
             check(self._lib.shm_vae_score(self._h, C.byref(src.struct), _ptr(idx), _ptr(n_dev), _ptr(eps), n, _ptr(score),
                                           _ptr(mu), _ptr(lv), _ptr(recon), _ptr(cnn_in), _stream()), "shm_vae_score")
