@@ -1,11 +1,632 @@
-// Tensor-core engine of the fused LSTM-VAE scorer (work in progress: not yet selectable).
+// Tensor-core engine (SHM_ENGINE_TC_BF16X3) of the fused LSTM-VAE scorer.
+//
+// Same math and same fusion as vae_fp32.cuh (TemporalVAE.forward + per-window MSE,
+// 4DOF/Scripts/Models/temporal_vae.py:51-77, 04_vae_thresholding.py:113-124), but every gate
+// pre-activation GEMM runs on the 5th-gen tensor cores:
+//
+//   * tcgen05.mma.kind::f16, M = 128 windows x N = 128 (32 hidden units x 4 gates) x K = 16, fp32
+//     accumulators in TMEM.  fp32-grade accuracy (the 1e-4 score tolerance rules out plain bf16/tf32,
+//     SURVEY.md section 7) comes from a 3-pass split: x = hi + lo, D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo,
+//     with fp16 halves (2^-22 operand error) for the bounded operands -- hidden states, decoder input,
+//     weights -- and bf16 halves (2^-17) only for the raw window values, whose range is unbounded.
+//   * the recurrent operand h_{t-1} never leaves the SM: the epilogue writes h_t (hi|lo) straight back
+//     into TMEM with tcgen05.st and the next step's MMAs read A from TMEM (the ".ts" form).
+//   * the layer input (x_t, the lower layer's h_t stream, or the constant decoder input u) is an
+//     A operand in shared memory (K-major, no-swizzle core-matrix image).
+//   * weights (pre-scaled by -log2(e) / -2log2(e) so the accumulator is directly the ex2 argument)
+//     stream L2 -> smem through a 4-stage ring of 1-D bulk async copies (TMA engine) gated by mbarriers.
+//   * warp-specialised persistent CTA (one per SM): 8 epilogue warps (LSTM cell in registers,
+//     ex2/rcp with merged divisions: 7 MUFU per cell), 1 copy-producer warp, 1 MMA-issuer warp,
+//     1 window-staging warp.  Two 128-column accumulator buffers let chunk c+1's MMAs overlap chunk c's
+//     cell update; the input-projection MMAs of step t+1 overlap the tail of step t.
+//   * layers of a stack run one after the other over all T steps; the lower layer's h_t stream goes
+//     through a per-CTA global scratch (written once, read once by bulk copies).
+#include "tcgen05.cuh"
 #include "vae_tc.cuh"
 
 namespace shm {
+using namespace tc;
 
-bool vae_tc_supported(const shm_vae_cfg&) { return false; }
-int vae_tc_alloc(VaeTc*, const shm_vae_cfg&) { return SHM_ERR_UNSUPPORTED; }
-int vae_tc_pack(VaeTc*, const shm_vae_cfg&, const VaeTcRaw&, cudaStream_t) { return SHM_ERR_UNSUPPORTED; }
+constexpr int TCM = 128;                       // windows per tile (UMMA M)
+constexpr int TC_NST = 4;                      // weight ring stages
+constexpr int TC_STAGE = 128 * 64 * 2;         // bytes per stage: [128 N-rows x 64 K] bf16
+constexpr int TC_XSTAGE = 128 * 16 * 2;        // [128 x 16] bf16 (window-input tiles)
+constexpr int TC_WARP_PROD = 8, TC_WARP_MMA = 9, TC_WARP_AUX = 10;
+constexpr int TC_THREADS = 11 * 32;          // warps 0-7 epilogue, 8 copy producer, 9 MMA issuer, 10 window staging
+constexpr int TC_EPI_THREADS = 256;
+constexpr float NLOG2E = -1.4426950408889634f;
+
+enum { IN_X = 0, IN_STREAM = 1, IN_CONST = 2 };
+enum { SINK_STREAM = 0, SINK_LAST_ENC = 1, SINK_LAST_DEC = 2 };
+
+struct TcPassDev {
+    const unsigned char* w;     // per chunk: [in part][hh part]; part = [kt][hi|lo] stage images
+    const float* bias;          // [H][4] pre-scaled b_ih + b_hh
+    int in_kind, sink;
+};
+struct TcDev {
+    TcPassDev pass[2 * SHM_MAX_L];
+    int n_pass, L;
+    unsigned char* scratch;     // per-CTA h_t stream: [grid][T][hi|lo image]
+    unsigned long long scratch_stride;
+    int n_tiles_max;
+};
+
+template <int H>
+struct TcSmem {
+    static constexpr int NCH = H / 32;
+    static constexpr int IMGH = TCM * H * 2;                // one bf16 image [128 x H]
+    static constexpr int IMG = 2 * IMGH;                    // hi + lo
+    static constexpr int off_ring = 0;
+    static constexpr int off_in = off_ring + TC_NST * TC_STAGE;
+    static constexpr int off_part = off_in + 2 * IMG;       // xhat partials [2][16][128] fp32
+    static constexpr int off_bias = off_part + 2 * 16 * TCM * 4;
+    static constexpr int off_wo = off_bias + H * 4 * 4;     // [H][16] fp32 + bias[16]
+    static constexpr int off_bar = off_wo + H * 16 * 4 + 64;
+    static constexpr int total = off_bar + 32 * 8 + 16;
+    static_assert(total <= 232448, "shared memory budget");
+};
+
+struct TcBars {
+    uint64_t w_full[TC_NST], w_empty[TC_NST], in_full[2], in_empty[2], acc_full[2], acc_empty[2], h_full[2];
+};
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// LSTM cell from pre-scaled gate arguments (ai = -log2e*a_i, af, ao likewise, ag = -2log2e*a_g):
+// sigma(a) = 1/(1+2^ai), tanh(a) = (1-2^ag)/(1+2^ag); the three divisions of c' = f*c + i*g share one
+// reciprocal, the two of h = o*tanh(c') another: 5 ex2 + 2 rcp per cell.
+__device__ __forceinline__ void lstm_cell(float ai, float af, float ag, float ao, float& c, float& h) {
+    const float ei = ex2_approx(fminf(ai, 30.f));
+    const float ef = ex2_approx(fminf(af, 30.f));
+    const float eg = ex2_approx(fminf(ag, 30.f));
+    const float eo = ex2_approx(fminf(ao, 30.f));
+    const float a = 1.f + ei, b = 1.f + ef, d = 1.f + eg, n = 2.f - d;
+    const float P = a * d;
+    const float num = fmaf(c, P, n * b);
+    c = num * rcp_approx(P * b);
+    const float ec = ex2_approx(fminf(c * (2.f * NLOG2E), 30.f));
+    const float q = 1.f + ec;
+    h = (2.f - q) * rcp_approx((1.f + eo) * q);
+}
+
+struct EpiCtx {
+    TcBars* bars;
+    uint32_t t_acc, hbuf, lane_base;
+    const float* bias_s;
+    const float* wo_s;
+    unsigned char* img;          // scratch image of this step (SINK_STREAM)
+    float* hT;                   // fp32 h_T [H][128] (SINK_LAST_ENC)
+    int wg, row, lane, sink;
+    bool last_step;
+};
+
+// One chunk (32 hidden units x 4 gates) of one step for this thread's (row, 16-unit) slice, in two batches of
+// 8 units to bound register pressure: TMEM -> registers, LSTM cell, h_t -> TMEM (bf16 hi|lo) and the pass's sink.
+template <int H, int C>
+__device__ __forceinline__ void epi_chunk(const EpiCtx& x, uint32_t& nacc, float (&cst)[16], float (&xh)[16]) {
+    using S = TcSmem<H>;
+    constexpr int b = C & 1;
+    mbar_wait(&x.bars->acc_full[b], nacc & 1);
+    ++nacc;
+    tc_fence_after_sync();
+    const int ub = C * 32 + x.wg * 16;                              // first hidden unit of this thread's slice
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t g0[8], g1[8], g2[8], g3[8];
+        const uint32_t abase = x.t_acc + x.lane_base + (uint32_t)(b * 128 + x.wg * 16 + half * 8);
+        tmem_ld8(abase + 0, g0);
+        tmem_ld8(abase + 32, g1);
+        tmem_ld8(abase + 64, g2);
+        tmem_ld8(abase + 96, g3);
+        tmem_ld_wait();
+        if (half == 1) {                                             // accumulator slice fully in registers: release it
+            tc_fence_before_sync();
+            __syncwarp();
+            if (x.lane == 0) mbar_arrive(&x.bars->acc_empty[b]);
+        }
+        const int u0 = ub + half * 8;
+        float hv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 bb = *reinterpret_cast<const float4*>(x.bias_s + (u0 + u) * 4);
+            lstm_cell(__uint_as_float(g0[u]) + bb.x, __uint_as_float(g1[u]) + bb.y, __uint_as_float(g2[u]) + bb.z,
+                      __uint_as_float(g3[u]) + bb.w, cst[half * 8 + u], hv[u]);
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_f16x2(hv[2 * j], hv[2 * j + 1], hi[j], lo[j]);
+        tmem_st4(x.hbuf + x.lane_base + (uint32_t)(u0 >> 1), hi);
+        tmem_st4(x.hbuf + x.lane_base + (uint32_t)(H / 2 + (u0 >> 1)), lo);
+        if (x.sink == SINK_STREAM) {
+            const int off = ((u0 >> 3) * 16 + (x.row >> 3)) * 128 + (x.row & 7) * 16;
+            *reinterpret_cast<uint4*>(x.img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(x.img + S::IMGH + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        } else if (x.sink == SINK_LAST_ENC) {
+            if (x.last_step) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x.hT[(u0 + u) * TCM + x.row] = hv[u];
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float4* wv = reinterpret_cast<const float4*>(x.wo_s + (u0 + u) * 16);
+                const float4 w0 = wv[0], w1 = wv[1], w2 = wv[2], w3 = wv[3];
+                xh[0] = fmaf(hv[u], w0.x, xh[0]); xh[1] = fmaf(hv[u], w0.y, xh[1]); xh[2] = fmaf(hv[u], w0.z, xh[2]); xh[3] = fmaf(hv[u], w0.w, xh[3]);
+                xh[4] = fmaf(hv[u], w1.x, xh[4]); xh[5] = fmaf(hv[u], w1.y, xh[5]); xh[6] = fmaf(hv[u], w1.z, xh[6]); xh[7] = fmaf(hv[u], w1.w, xh[7]);
+                xh[8] = fmaf(hv[u], w2.x, xh[8]); xh[9] = fmaf(hv[u], w2.y, xh[9]); xh[10] = fmaf(hv[u], w2.z, xh[10]); xh[11] = fmaf(hv[u], w2.w, xh[11]);
+                xh[12] = fmaf(hv[u], w3.x, xh[12]); xh[13] = fmaf(hv[u], w3.y, xh[13]); xh[14] = fmaf(hv[u], w3.z, xh[14]); xh[15] = fmaf(hv[u], w3.w, xh[15]);
+            }
+        }
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
+    using S = TcSmem<H>;
+    constexpr int NCH = S::NCH;
+    constexpr int NFIRST = NCH < 2 ? NCH : 2;
+    constexpr int KT_PER_PART = H / 64;                      // 64-wide K tiles per H-wide part
+    constexpr uint32_t IDESC_H = make_idesc_f16(128, 128);      // fp16 hi|lo operands (h, u, weights)
+    constexpr uint32_t IDESC_X = make_idesc_bf16(128, 128);     // bf16 hi|lo for the raw-window operand (unbounded range)
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* ring = smem + S::off_ring;
+    unsigned char* inbuf = smem + S::off_in;
+    float* part_s = reinterpret_cast<float*>(smem + S::off_part);
+    float* bias_s = reinterpret_cast<float*>(smem + S::off_bias);
+    float* wo_s = reinterpret_cast<float*>(smem + S::off_wo);
+    float* bo_s = wo_s + H * 16;
+    TcBars* bars = reinterpret_cast<TcBars*>(smem + S::off_bar);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + S::off_bar + 32 * 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = src.T;
+    long long n_eff = io.n;
+    if (io.n_dev) n_eff = min(n_eff, (long long)__ldg(io.n_dev));
+    const int n_tiles = (int)((n_eff + TCM - 1) / TCM);
+
+    if (tid == 0) {
+        for (int i = 0; i < TC_NST; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 1);
+            mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 8);
+            mbar_init(&bars->h_full[i], 8);
+        }
+        fence_mbar_init();
+    }
+    if (warp == TC_WARP_MMA) tmem_alloc(tmem_holder, 512);
+    for (int i = tid; i < P.D * H; i += TC_THREADS) { const int d = i / H, k = i - d * H; wo_s[k * 16 + d] = __ldg(P.out_w + i); }
+    if (tid < 16) bo_s[tid] = tid < P.D ? __ldg(P.out_b + tid) : 0.f;
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tbase = *tmem_holder;
+    const uint32_t t_acc = tbase;                 // 2 x 128 accumulator columns
+    const uint32_t t_h = tbase + 256;             // 2 x H columns: h_t as bf16 pairs, [hi H/2 | lo H/2]
+
+    unsigned char* scratch = TC.scratch + (size_t)blockIdx.x * TC.scratch_stride;
+
+    // register budget: the epilogue warpgroups hold the cell state + a full accumulator slice
+
+    // Use-counters of the mbarriers.  Every thread carries the same pass-entry values ("base") and
+    // advances them analytically at the end of each pass, so roles that skip a barrier in one pass
+    // still know its phase in the next; inside a pass each role counts its own uses from the base.
+    uint32_t ring_base = 0, in_base[2] = {0, 0}, acc_base[2] = {0, 0}, h_base[2] = {0, 0};
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long n0 = (long long)tile * TCM;
+        const int nvalid = (int)min((long long)TCM, n_eff - n0);
+        int hT_buf = 1;                            // in-buffer that receives the encoder's fp32 h_T
+        float sse = 0.f;                           // per-row squared error (epilogue warps 0-3)
+
+        for (int p = 0; p < TC.n_pass; ++p) {
+            const TcPassDev ps = TC.pass[p];
+            const int in_kind = ps.in_kind, sink = ps.sink;
+            if (sink == SINK_LAST_ENC) hT_buf = (in_kind == IN_STREAM) ? (T & 1) : 1;
+            const int u_buf = hT_buf ^ 1;
+            const int part_in_bytes = (in_kind == IN_X) ? 2 * TC_XSTAGE : KT_PER_PART * 2 * TC_STAGE;
+            const int part_hh_bytes = KT_PER_PART * 2 * TC_STAGE;
+            uint32_t ring_it = ring_base, n_in[2] = {in_base[0], in_base[1]}, n_acc[2] = {acc_base[0], acc_base[1]},
+                     n_h[2] = {h_base[0], h_base[1]};
+            (void)ring_it; (void)n_in; (void)n_acc; (void)n_h;
+
+            // ------------------------------------------------------------------ heads (between the stacks)
+            if (p == TC.L && warp < 8) {
+                float* hT = reinterpret_cast<float*>(inbuf + hT_buf * S::IMG);      // [H][128] fp32
+                float* muS = reinterpret_cast<float*>(ring);                        // [2Z][128]
+                float* zS = muS + 2 * VAE_MAX_Z * TCM;                              // [Z][128]
+                if (P.has_ln) {
+                    if (tid < TCM) {
+                        float m = 0.f;
+                        for (int k = 0; k < H; ++k) m += hT[k * TCM + tid];
+                        m /= (float)H;
+                        float v = 0.f;
+                        for (int k = 0; k < H; ++k) { const float d = hT[k * TCM + tid] - m; v = fmaf(d, d, v); }
+                        v /= (float)H;
+                        const float rstd = 1.0f / sqrtf(v + P.ln_eps);
+                        for (int k = 0; k < H; ++k)
+                            hT[k * TCM + tid] = fmaf((hT[k * TCM + tid] - m) * rstd, __ldg(P.ln_w + k), __ldg(P.ln_b + k));
+                    }
+                    epi_bar_sync();
+                }
+                for (int item = tid; item < 2 * P.Z * TCM; item += TC_EPI_THREADS) {
+                    const int o = item / TCM, w = item - o * TCM;
+                    const bool is_lv = o >= P.Z;
+                    const int zi = is_lv ? o - P.Z : o;
+                    const float* wr = (is_lv ? P.lv_w : P.mu_w) + zi * H;
+                    float y = __ldg((is_lv ? P.lv_b : P.mu_b) + zi);
+                    for (int k = 0; k < H; ++k) y = fmaf(hT[k * TCM + w], __ldg(wr + k), y);
+                    muS[o * TCM + w] = y;
+                    if (w < nvalid) {
+                        float* dst = is_lv ? io.logvar : io.mu;
+                        if (dst) dst[(n0 + w) * P.Z + zi] = y;
+                    }
+                }
+                epi_bar_sync();
+                for (int item = tid; item < P.Z * TCM; item += TC_EPI_THREADS) {
+                    const int zi = item / TCM, w = item - zi * TCM;
+                    const float m = muS[zi * TCM + w], lv = muS[(P.Z + zi) * TCM + w];
+                    float z = m;
+                    if (io.eps && w < nvalid) z = fmaf(__ldg(io.eps + (n0 + w) * P.Z + zi), expf(0.5f * lv), m);
+                    zS[zi * TCM + w] = z;
+                }
+                epi_bar_sync();
+                // u = tanh(W z + b) as the decoder's constant A operand: bf16 hi|lo K-major images
+                unsigned short* uhi = reinterpret_cast<unsigned short*>(inbuf + u_buf * S::IMG);
+                unsigned short* ulo = reinterpret_cast<unsigned short*>(inbuf + u_buf * S::IMG + S::IMGH);
+                for (int item = tid; item < H * TCM; item += TC_EPI_THREADS) {
+                    const int k = item / TCM, w = item - k * TCM;
+                    float y = __ldg(P.l2h_b + k);
+                    const float* wr = P.l2h_w + k * P.Z;
+                    for (int zi = 0; zi < P.Z; ++zi) y = fmaf(zS[zi * TCM + w], __ldg(wr + zi), y);
+                    const float u = tanhf(y);
+                    const __half bh = __float2half_rn(u);
+                    const __half bl = __float2half_rn(u - __half2float(bh));
+                    const int off = ((k >> 3) * 16 + (w >> 3)) * 64 + (w & 7) * 8 + (k & 7);
+                    uhi[off] = *reinterpret_cast<const unsigned short*>(&bh);
+                    ulo[off] = *reinterpret_cast<const unsigned short*>(&bl);
+                }
+                fence_proxy_async_smem();
+            }
+            const bool encode_only = (p == TC.L) && !io.score && !io.recon && !io.cnn_in;
+            __syncthreads();                       // (A) previous pass / heads complete and visible
+            if (encode_only) break;
+
+            if (warp < 8) {
+                // =============================================================== epilogue warps
+                const int wg = warp >> 2;                                  // units [16*wg, 16*wg+16) of each chunk
+                const int row = (warp & 3) * 32 + lane;                    // TMEM lane == window row
+                const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+                for (int i = tid; i < H * 4; i += TC_EPI_THREADS) bias_s[i] = __ldg(ps.bias + i);
+                epi_bar_sync();
+                float cst[NCH][16];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) cst[c][u] = 0.f;
+                uint32_t nacc0 = n_acc[0], nacc1 = n_acc[1];
+
+                for (int t = 0; t < T; ++t) {
+                    float xh[16];
+#pragma unroll
+                    for (int d = 0; d < 16; ++d) xh[d] = 0.f;
+                    const uint32_t hbuf = t_h + (uint32_t)((t & 1) * H);
+                    EpiCtx ctx{bars, t_acc, hbuf, lane_base, bias_s, wo_s, scratch + (size_t)t * S::IMG,
+                               reinterpret_cast<float*>(inbuf + hT_buf * S::IMG), wg, row, lane, sink, t == T - 1};
+                    epi_chunk<H, 0>(ctx, nacc0, cst[0], xh);
+                    if constexpr (NCH > 1) epi_chunk<H, 1>(ctx, nacc1, cst[1], xh);
+                    if constexpr (NCH > 2) epi_chunk<H, 2>(ctx, nacc0, cst[2], xh);
+                    if constexpr (NCH > 3) epi_chunk<H, 3>(ctx, nacc1, cst[3], xh);
+                    tmem_st_wait();
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->h_full[t & 1]);
+
+                    if (sink == SINK_LAST_DEC) {
+                        // xhat_t = W_o h_t + b_o : combine the two unit halves, then the squared error of this row
+                        float* ps_ = part_s + (t & 1) * 16 * TCM;
+                        if (wg == 1) {
+#pragma unroll
+                            for (int d = 0; d < 16; ++d) ps_[d * TCM + row] = xh[d];
+                        }
+                        epi_bar_sync();
+                        if (wg == 0) {
+                            const bool valid = row < nvalid;
+                            const long long n = n0 + row;
+                            const long long win = (valid && io.idx) ? (long long)io.idx[n] : n;
+                            for (int d = 0; d < P.D; ++d) {
+                                const float y = xh[d] + ps_[d * TCM + row] + bo_s[d];
+                                const float x = valid ? win_fetch(src, win, t, d) : 0.f;
+                                const float e = x - y;
+                                sse = fmaf(e, e, sse);
+                                if (valid) {
+                                    if (io.recon) io.recon[(n * T + t) * P.D + d] = y;
+                                    if (io.cnn_in) {
+                                        io.cnn_in[((n * 2 + 0) * T + t) * P.D + d] = x;
+                                        io.cnn_in[((n * 2 + 1) * T + t) * P.D + d] = e * e;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                if (sink == SINK_STREAM) fence_proxy_async_all();          // scratch writes -> visible to the bulk-copy engine
+                if (sink == SINK_LAST_DEC && wg == 0 && row < nvalid && io.score) io.score[n0 + row] = sse / (float)(T * P.D);
+            } else if (warp == TC_WARP_PROD) {
+                // =============================================================== copy producer (one lane)
+                if (lane == 0) {
+                    auto load_stage = [&](const unsigned char* g, uint32_t bytes) {
+                        const uint32_t slot = ring_it % TC_NST;
+                        mbar_wait(&bars->w_empty[slot], ((ring_it / TC_NST) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&bars->w_full[slot], bytes);
+                        bulk_g2s(ring + slot * TC_STAGE, g, bytes, &bars->w_full[slot]);
+                        ++ring_it;
+                    };
+                    auto load_part = [&](const unsigned char* g, int nstage, uint32_t bytes) {
+                        for (int s = 0; s < nstage; ++s) load_stage(g + (size_t)s * bytes, bytes);
+                    };
+                    auto load_in = [&](int t) {
+                        const int b = t & 1;
+                        mbar_wait(&bars->in_empty[b], (n_in[b] & 1) ^ 1);
+                        ++n_in[b];
+                        mbar_arrive_expect_tx(&bars->in_full[b], (uint32_t)S::IMG);
+                        const unsigned char* g = scratch + (size_t)t * S::IMG;
+                        for (int q = 0; q < S::IMG / 16384; ++q)
+                            bulk_g2s(inbuf + b * S::IMG + q * 16384, g + q * 16384, 16384, &bars->in_full[b]);
+                    };
+                    const int in_nst = (in_kind == IN_X) ? 2 : KT_PER_PART * 2;
+                    const uint32_t in_sb = (in_kind == IN_X) ? TC_XSTAGE : TC_STAGE;
+                    const size_t chunk_bytes = (size_t)part_in_bytes + part_hh_bytes;
+                    if (in_kind == IN_STREAM) load_in(0);
+                    for (int t = 0; t < T; ++t) {
+                        if (in_kind == IN_STREAM && t + 1 < T) load_in(t + 1);
+                        for (int c = 0; c < NFIRST; ++c) load_part(ps.w + c * chunk_bytes, in_nst, in_sb);
+                        for (int c = 0; c < NCH; ++c) {
+                            if (c >= NFIRST) load_part(ps.w + c * chunk_bytes, in_nst, in_sb);
+                            if (t > 0) load_part(ps.w + c * chunk_bytes + part_in_bytes, KT_PER_PART * 2, TC_STAGE);
+                        }
+                    }
+                }
+            } else if (warp == TC_WARP_MMA) {
+                // =============================================================== MMA issuer (one lane)
+                if (lane == 0) {
+                    const uint32_t ring_a = smem_u32(ring);
+                    // one part = accumulate  A[128 x K] * W_part^T  into acc: A from smem (layer input) or TMEM (h_{t-1})
+                    auto do_part = [&](bool is_in, int c, int t, uint32_t first_acc) {
+                        const uint32_t acc = t_acc + (uint32_t)((c & 1) * 128);
+                        const bool xin = is_in && in_kind == IN_X;
+                        const int kper = xin ? 1 : 4;
+                        const int nkt = xin ? 1 : KT_PER_PART;
+                        uint32_t a_hi_s = 0, a_lo_s = 0, a_hi_t = 0, a_lo_t = 0;
+                        if (is_in) {
+                            if (xin) { a_hi_s = smem_u32(inbuf) + (t & 1) * 2 * TC_XSTAGE; a_lo_s = a_hi_s + TC_XSTAGE; }
+                            else {
+                                const int b = (in_kind == IN_CONST) ? u_buf : (t & 1);
+                                a_hi_s = smem_u32(inbuf) + b * S::IMG; a_lo_s = a_hi_s + S::IMGH;
+                            }
+                        } else {
+                            a_hi_t = t_h + (uint32_t)(((t - 1) & 1) * H); a_lo_t = a_hi_t + H / 2;
+                        }
+                        uint32_t accf = first_acc;
+                        const uint32_t IDESC = xin ? IDESC_X : IDESC_H;
+                        for (int kt = 0; kt < nkt; ++kt) {
+#pragma unroll
+                            for (int half = 0; half < 2; ++half) {           // 0: B_hi stage (A_hi and A_lo), 1: B_lo stage (A_hi)
+                                const uint32_t slot = ring_it % TC_NST;
+                                mbar_wait(&bars->w_full[slot], (ring_it / TC_NST) & 1);
+                                tc_fence_after_sync();
+                                for (int j = 0; j < kper; ++j) {
+                                    const int k = kt * kper + j;               // k-step (16 elements)
+                                    const uint64_t bdesc = make_smem_desc(ring_a + slot * TC_STAGE + j * 4096, 2048, 128);
+                                    if (is_in) {
+                                        mma_ss(acc, make_smem_desc(a_hi_s + k * 4096, 2048, 128), bdesc, IDESC, accf);
+                                        accf = 1;
+                                        if (half == 0) mma_ss(acc, make_smem_desc(a_lo_s + k * 4096, 2048, 128), bdesc, IDESC, 1);
+                                    } else {
+                                        mma_ts(acc, a_hi_t + k * 8, bdesc, IDESC, accf);
+                                        accf = 1;
+                                        if (half == 0) mma_ts(acc, a_lo_t + k * 8, bdesc, IDESC, 1);
+                                    }
+                                }
+                                mma_commit(&bars->w_empty[slot]);
+                                ++ring_it;
+                            }
+                        }
+                    };
+                    for (int t = 0; t < T; ++t) {
+                        if (in_kind != IN_CONST) {
+                            mbar_wait(&bars->in_full[t & 1], n_in[t & 1] & 1);
+                            ++n_in[t & 1];
+                            tc_fence_after_sync();
+                        }
+                        for (int c = 0; c < NFIRST; ++c) {
+                            mbar_wait(&bars->acc_empty[c & 1], (n_acc[c & 1] & 1) ^ 1);
+                            ++n_acc[c & 1];
+                            tc_fence_after_sync();
+                            do_part(true, c, t, 0);
+                        }
+                        if (NCH <= NFIRST && in_kind != IN_CONST) mma_commit(&bars->in_empty[t & 1]);
+                        if (t > 0) {
+                            mbar_wait(&bars->h_full[(t - 1) & 1], n_h[(t - 1) & 1] & 1);
+                            ++n_h[(t - 1) & 1];
+                            tc_fence_after_sync();
+                        }
+                        for (int c = 0; c < NCH; ++c) {
+                            if (c >= NFIRST) {
+                                mbar_wait(&bars->acc_empty[c & 1], (n_acc[c & 1] & 1) ^ 1);
+                                ++n_acc[c & 1];
+                                tc_fence_after_sync();
+                                do_part(true, c, t, 0);
+                                if (c == NCH - 1 && in_kind != IN_CONST) mma_commit(&bars->in_empty[t & 1]);
+                            }
+                            if (t > 0) do_part(false, c, t, 1);
+                            mma_commit(&bars->acc_full[c & 1]);
+                        }
+                    }
+                    // the last step's h_full arrivals are never consumed by an MMA: consume them here so the
+                    // phase bookkeeping stays aligned for the next pass
+                    mbar_wait(&bars->h_full[(T - 1) & 1], n_h[(T - 1) & 1] & 1);
+                    ++n_h[(T - 1) & 1];
+                }
+            } else if (warp == TC_WARP_AUX) {
+                // =============================================================== window staging: x_t -> bf16 hi|lo A image
+                if (in_kind == IN_X) {
+                    for (int t = 0; t < T; ++t) {
+                        const int b = t & 1;
+                        mbar_wait(&bars->in_empty[b], (n_in[b] & 1) ^ 1);
+                        ++n_in[b];
+                        unsigned char* xhi = inbuf + b * 2 * TC_XSTAGE;
+                        unsigned char* xlo = xhi + TC_XSTAGE;
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) {
+                            const int row = rr * 32 + lane;
+                            float v[16];
+#pragma unroll
+                            for (int d = 0; d < 16; ++d) v[d] = 0.f;
+                            if (row < nvalid) {
+                                const long long n = n0 + row;
+                                const long long win = io.idx ? (long long)io.idx[n] : n;
+                                for (int d = 0; d < P.D; ++d) v[d] = win_fetch(src, win, t, d);
+                            }
+                            uint32_t hi[8], lo[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const int off = (q * 16 + (row >> 3)) * 128 + (row & 7) * 16;
+                                *reinterpret_cast<uint4*>(xhi + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                                *reinterpret_cast<uint4*>(xlo + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->in_full[b]);
+                    }
+                }
+            }
+            __syncthreads();                       // (B) end of pass
+            {
+                const uint32_t stages_step0 = (uint32_t)NCH * ((in_kind == IN_X) ? 2 : KT_PER_PART * 2);
+                const uint32_t stages_step = stages_step0 + (uint32_t)NCH * KT_PER_PART * 2;
+                ring_base += stages_step0 + (uint32_t)(T - 1) * stages_step;
+                const uint32_t even = (uint32_t)((T + 1) / 2), odd = (uint32_t)(T / 2);
+                if (in_kind != IN_CONST) { in_base[0] += even; in_base[1] += odd; }
+                acc_base[0] += (uint32_t)T * ((NCH + 1) / 2);
+                acc_base[1] += (uint32_t)T * (NCH / 2);
+                h_base[0] += even; h_base[1] += odd;
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == TC_WARP_MMA) tmem_dealloc(tbase, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight repacking: state_dict fp32 -> pre-scaled bf16 hi|lo stage images in UMMA K-major layout
+//   out, per chunk c: [in part: kt x {hi,lo} images of [128 x KT_in]] [hh part: kt x {hi,lo} of [128 x 64]]
+//   N-row n of a chunk = gate (n / 32), hidden unit c*32 + n % 32.
+// ------------------------------------------------------------------------------------------------
+__global__ void tc_pack_pass_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, int Kin, int H,
+                                    int x_input, unsigned short* __restrict__ out, float* __restrict__ bias) {
+    const int NCH = H / 32;
+    const int Kin_pad = x_input ? 16 : H;
+    const int kt_in = x_input ? 16 : 64;
+    const int in_elems = 128 * Kin_pad * 2;              // hi + lo
+    const int hh_elems = 128 * H * 2;
+    const int chunk_elems = in_elems + hh_elems;
+    const int per_chunk_work = 128 * (Kin_pad + H);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NCH * per_chunk_work; i += gridDim.x * blockDim.x) {
+        const int c = i / per_chunk_work;
+        int r = i - c * per_chunk_work;
+        const int n = r / (Kin_pad + H);
+        const int kk = r - n * (Kin_pad + H);
+        const int gate = n >> 5;
+        const int row = gate * H + c * 32 + (n & 31);
+        const float scale = (gate == 2) ? 2.f * NLOG2E : NLOG2E;
+        float w;
+        int base, k, ktile;
+        if (kk < Kin_pad) {
+            k = kk; ktile = kt_in;
+            w = (k < Kin) ? w_ih[(size_t)row * Kin + k] : 0.f;
+            base = c * chunk_elems;
+        } else {
+            k = kk - Kin_pad; ktile = 64;
+            w = w_hh[(size_t)row * H + k];
+            base = c * chunk_elems + in_elems;
+        }
+        w *= scale;
+        unsigned short sh, sl;
+        if (x_input && kk < Kin_pad) {              // pairs with the bf16 window operand
+            const __nv_bfloat16 bh = __float2bfloat16_rn(w);
+            const __nv_bfloat16 bl = __float2bfloat16_rn(w - __bfloat162float(bh));
+            sh = *reinterpret_cast<const unsigned short*>(&bh); sl = *reinterpret_cast<const unsigned short*>(&bl);
+        } else {
+            const __half bh = __float2half_rn(w);
+            const __half bl = __float2half_rn(w - __half2float(bh));
+            sh = *reinterpret_cast<const unsigned short*>(&bh); sl = *reinterpret_cast<const unsigned short*>(&bl);
+        }
+        const int kt = k / ktile, kl = k - kt * ktile;
+        const int stage_elems = 128 * ktile;
+        const int off = base + kt * 2 * stage_elems + ((kl >> 3) * 16 + (n >> 3)) * 64 + (n & 7) * 8 + (kl & 7);
+        out[off] = sh;
+        out[off + stage_elems] = sl;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * H; i += gridDim.x * blockDim.x) {
+        const int u = i >> 2, g = i & 3;
+        const float scale = (g == 2) ? 2.f * NLOG2E : NLOG2E;
+        bias[i] = (b_ih[g * H + u] + b_hh[g * H + u]) * scale;
+    }
+}
+
+static size_t tc_pass_bytes(int H, bool x_input) { return (size_t)(H / 32) * 128 * ((x_input ? 16 : H) + H) * 2 * 2; }
+
+bool vae_tc_supported(const shm_vae_cfg& cfg) {
+    return (cfg.H == 128 || cfg.H == 64) && cfg.L >= 1 && cfg.L <= SHM_MAX_L && cfg.D <= 16 && cfg.Z <= VAE_MAX_Z;
+}
+
+int vae_tc_alloc(VaeTc* tc, const shm_vae_cfg& cfg) {
+    size_t bytes = 0;
+    for (int l = 0; l < cfg.L; ++l) bytes += tc_pass_bytes(cfg.H, l == 0) + tc_pass_bytes(cfg.H, false);
+    tc->wpack_bytes = bytes;
+    if (cudaMalloc(&tc->wpack, bytes) != cudaSuccess || cudaMalloc(&tc->bias, (size_t)2 * cfg.L * 4 * cfg.H * sizeof(float)) != cudaSuccess) {
+        set_cuda_error(cudaGetLastError(), "cudaMalloc(vae tc weights)");
+        return SHM_ERR_NOMEM;
+    }
+    cudaError_t e = cudaSuccess;
+    if (cfg.H == 128) e = cudaFuncSetAttribute(vae_score_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::total);
+    else e = cudaFuncSetAttribute(vae_score_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64>::total);
+    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(vae_score_tc)"); return SHM_ERR_CUDA; }
+    tc->H = cfg.H; tc->L = cfg.L; tc->D = cfg.D;
+    return SHM_OK;
+}
+
+int vae_tc_pack(VaeTc* tc, const shm_vae_cfg& cfg, const VaeTcRaw& raw, cudaStream_t st) {
+    const int H = cfg.H, L = cfg.L;
+    size_t off = 0;
+    for (int p = 0; p < 2 * L; ++p) {
+        const bool dec = p >= L;
+        const int l = dec ? p - L : p;
+        const bool xin = (!dec && l == 0);
+        const float* wih = dec ? raw.dec_wih[l] : raw.enc_wih[l];
+        const float* whh = dec ? raw.dec_whh[l] : raw.enc_whh[l];
+        const float* bih = dec ? raw.dec_bih[l] : raw.enc_bih[l];
+        const float* bhh = dec ? raw.dec_bhh[l] : raw.enc_bhh[l];
+        tc->pass_off[p] = off;
+        tc_pack_pass_kernel<<<296, 256, 0, st>>>(wih, whh, bih, bhh, xin ? cfg.D : H, H, xin ? 1 : 0,
+                                                 reinterpret_cast<unsigned short*>(static_cast<unsigned char*>(tc->wpack) + off),
+                                                 tc->bias + (size_t)p * 4 * H);
+        SHM_LAUNCH_CHECK();
+        off += tc_pass_bytes(H, xin);
+    }
+    return SHM_OK;
+}
+
 void vae_tc_free(VaeTc* tc) {
     if (!tc) return;
     if (tc->wpack) cudaFree(tc->wpack);
@@ -13,6 +634,39 @@ void vae_tc_free(VaeTc* tc) {
     if (tc->scratch) cudaFree(tc->scratch);
     tc->wpack = nullptr; tc->bias = nullptr; tc->scratch = nullptr;
 }
-int vae_tc_score(VaeTc*, const VaeDev&, const WinSrc&, const VaeIO&, cudaStream_t) { return SHM_ERR_UNSUPPORTED; }
+
+int vae_tc_score(VaeTc* tc, const VaeDev& P, const WinSrc& src, const VaeIO& io, cudaStream_t st) {
+    int dev = 0;
+    SHM_CUDA(cudaGetDevice(&dev));
+    const int H = tc->H, L = tc->L;
+    const long long tiles = (io.n + TCM - 1) / TCM;
+    const int grid = (int)min((long long)device_sm_count(dev), tiles);
+    const size_t img = (size_t)TCM * H * 2 * 2;
+    const size_t stride = (L > 1) ? img * (size_t)src.T : 0;
+    const size_t need = stride * (size_t)device_sm_count(dev);
+    if (need > tc->scratch_bytes) {
+        SHM_CUDA(cudaStreamSynchronize(st));
+        if (tc->scratch) cudaFree(tc->scratch);
+        tc->scratch = nullptr; tc->scratch_bytes = 0;
+        if (cudaMalloc(&tc->scratch, need) != cudaSuccess) { set_cuda_error(cudaGetLastError(), "cudaMalloc(vae tc scratch)"); return SHM_ERR_NOMEM; }
+        tc->scratch_bytes = need;
+    }
+    TcDev T;
+    memset(&T, 0, sizeof(T));
+    T.n_pass = 2 * L; T.L = L;
+    T.scratch = static_cast<unsigned char*>(tc->scratch); T.scratch_stride = stride;
+    for (int p = 0; p < 2 * L; ++p) {
+        const bool dec = p >= L;
+        const int l = dec ? p - L : p;
+        T.pass[p].w = static_cast<const unsigned char*>(tc->wpack) + tc->pass_off[p];
+        T.pass[p].bias = tc->bias + (size_t)p * 4 * H;
+        T.pass[p].in_kind = (l > 0) ? IN_STREAM : (dec ? IN_CONST : IN_X);
+        T.pass[p].sink = (l < L - 1) ? SINK_STREAM : (dec ? SINK_LAST_DEC : SINK_LAST_ENC);
+    }
+    if (H == 128) vae_score_tc_kernel<128><<<grid, TC_THREADS, TcSmem<128>::total, st>>>(P, T, src, io);
+    else vae_score_tc_kernel<64><<<grid, TC_THREADS, TcSmem<64>::total, st>>>(P, T, src, io);
+    SHM_LAUNCH_CHECK();
+    return SHM_OK;
+}
 
 }  // namespace shm

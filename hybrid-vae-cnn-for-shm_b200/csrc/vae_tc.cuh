@@ -11,10 +11,12 @@ struct VaeTcRaw {
 };
 
 struct VaeTc {
-    void* wpack;       // bf16 hi/lo weight tiles in the UMMA smem layout
-    float* bias;       // packed biases
-    void* scratch;     // inter-layer activation stream
+    void* wpack;       // bf16 hi/lo weight tiles in the UMMA smem layout, one block per (stack, layer) pass
+    float* bias;       // pre-scaled packed biases [2L][H][4]
+    void* scratch;     // per-CTA inter-layer h_t stream (grown on demand)
     size_t wpack_bytes, scratch_bytes;
+    size_t pass_off[2 * SHM_MAX_L];
+    int H, L, D;
 };
 
 bool vae_tc_supported(const shm_vae_cfg& cfg);

@@ -31,7 +31,7 @@ def flags_match_outside_band(score_gpu, score_ref, thr, flag_gpu):
 
 
 def engines():
-    return [ops.ENGINE_FP32]
+    return [ops.ENGINE_FP32, ops.ENGINE_TC_BF16X3]
 
 
 def to_dev(x, dev):
@@ -48,13 +48,24 @@ def test_vae_score_vs_golden_and_oracle(cuda_dev, golden_dir, stage, scale, engi
     sd = synth.stage_vae_weights(stage, seed=seed, scale=float(g["scale"]))
     X = synth.windows(N, s["T"], s["D"], seed=seed, amp=1.0 if scale == 1 else 2.5)
     eps = synth.eps(N, s["Z"], seed=seed)
+    if engine == ops.ENGINE_TC_BF16X3 and stage == "1dof":
+        with pytest.raises(ops.ShmfastError):          # H=32 is served by the fp32 engine only
+            ops.VaeScorer(sd, cuda_dev, engine=engine)
+        return
     vae = ops.VaeScorer(sd, cuda_dev, engine=engine)
+    assert vae.engine == engine
     out = vae.score(ops.WindowSource(to_dev(X, cuda_dev), s["T"]), to_dev(eps, cuda_dev), want_latent=True, want_recon=True)
     score = out["score"].cpu().numpy()
     # against the reference module's own outputs
+    print(f"{stage} s{scale} engine={engine}: score rel err {rel_err(score, g['score']):.2e}, "
+          f"mu abs err {np.abs(out['mu'].cpu().numpy() - g['mu']).max():.2e}, "
+          f"recon abs err {np.abs(out['recon'].cpu().numpy()[:8] - g['recon']).max():.2e}")
     assert rel_err(score, g["score"]) < REL_TOL
-    assert np.allclose(out["mu"].cpu().numpy(), g["mu"], rtol=REL_TOL, atol=2e-5)
-    assert np.allclose(out["logvar"].cpu().numpy(), g["logvar"], rtol=REL_TOL, atol=2e-5)
+    # latent heads sit behind a LayerNorm that amplifies absolute error: 2e-5 for the fp32 engine, 1e-4 for
+    # the 3-pass bf16 split (2^-17 operand error); the contract (north_star) is on scores and logits
+    lat_atol = 2e-5 if engine == ops.ENGINE_FP32 else 1e-4
+    assert np.allclose(out["mu"].cpu().numpy(), g["mu"], rtol=REL_TOL, atol=lat_atol)
+    assert np.allclose(out["logvar"].cpu().numpy(), g["logvar"], rtol=REL_TOL, atol=lat_atol)
     assert np.allclose(out["recon"].cpu().numpy()[:8], g["recon"], rtol=REL_TOL, atol=1e-4)
     # against the oracle on the same inputs
     recon_o, mu_o, lv_o = O.vae_forward(sd, X, eps, np.float64)
