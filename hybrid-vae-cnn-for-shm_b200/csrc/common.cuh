@@ -46,6 +46,7 @@ struct WinSrc {
     float clip;
     float mean[SHM_MAX_D];
     float std[SHM_MAX_D];
+    float rstd[SHM_MAX_D];      // 1/std, for the division-free transform of the tensor-core scorer
 };
 
 inline int make_winsrc(const shm_window_src* s, WinSrc* w) {
@@ -56,6 +57,7 @@ inline int make_winsrc(const shm_window_src* s, WinSrc* w) {
         w->chan[i] = i < s->D ? s->chan[i] : 0;
         w->mean[i] = i < s->D ? s->mean[i] : 0.f;
         w->std[i] = i < s->D ? s->std[i] : 1.f;
+        w->rstd[i] = (float)(1.0 / (double)w->std[i]);
         if (i < s->D && s->chan[i] < 0) return SHM_ERR_ARG;
     }
     return SHM_OK;
@@ -67,6 +69,23 @@ __device__ __forceinline__ float win_transform(const WinSrc& s, float raw, int d
     float x = raw;
     if (s.normalize) x = __fdiv_rn(__fsub_rn(raw, s.mean[d]), s.std[d]);
     if (s.clip > 0.f) x = (x < -s.clip) ? -s.clip : ((x > s.clip) ? s.clip : x);   // NaN passes, as np.clip
+    if (s.nan_to_zero && !isfinite(x)) x = 0.f;
+    return x;
+}
+
+// Same transform without the IEEE-divide subroutine: q = (x-m)*rstd refined by one Newton step (the result is
+// the correctly rounded quotient except in rare last-bit cases).  Used where the value only feeds the
+// tolerance-checked score, never where windows are handed back to the caller.
+__device__ __forceinline__ float win_transform_fast(const WinSrc& s, float raw, int d) {
+    float x = raw;
+    if (s.normalize) {
+        const float num = raw - s.mean[d];
+        const float q = num * s.rstd[d];
+        const float r = fmaf(-q, s.std[d], num);
+        const float q2 = fmaf(r, s.rstd[d], q);
+        x = isfinite(q2) ? q2 : q;
+    }
+    if (s.clip > 0.f) x = (x < -s.clip) ? -s.clip : ((x > s.clip) ? s.clip : x);
     if (s.nan_to_zero && !isfinite(x)) x = 0.f;
     return x;
 }

@@ -217,6 +217,21 @@ extern "C" int shm_vae_destroy(shm_vae* h) {
 
 extern "C" int shm_vae_engine(const shm_vae* h) { return h ? h->engine : SHM_ERR_ARG; }
 
+extern "C" int shm_vae_debug_counters(shm_vae* h, long long* out_host, int n) {
+    if (!h || n < 0) return SHM_ERR_ARG;
+    if (h->engine != SHM_ENGINE_TC_BF16X3) return SHM_ERR_UNSUPPORTED;
+    const size_t total = (size_t)256 * 3 * 8;
+    if (!h->tc.dbg) {                       // first call switches the counters on
+        SHM_CUDA(cudaMalloc(&h->tc.dbg, total * sizeof(long long)));
+        SHM_CUDA(cudaMemset(h->tc.dbg, 0, total * sizeof(long long)));
+    }
+    if (out_host && n > 0) {
+        SHM_CUDA(cudaDeviceSynchronize());
+        SHM_CUDA(cudaMemcpy(out_host, h->tc.dbg, (size_t)(n < (int)total ? n : (int)total) * sizeof(long long), cudaMemcpyDeviceToHost));
+    }
+    return SHM_OK;
+}
+
 static int vae_launch(shm_vae* h, const shm::WinSrc& src, const shm::VaeIO& io, cudaStream_t st) {
     if (h->engine == SHM_ENGINE_TC_BF16X3 && !io.z_in) return vae_tc_score(&h->tc, h->dev, src, io, st);
     const int H = h->cfg.H;

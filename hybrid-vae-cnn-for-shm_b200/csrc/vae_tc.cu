@@ -31,8 +31,9 @@ constexpr int TCM = 128;                       // windows per tile (UMMA M)
 constexpr int TC_NST = 4;                      // weight ring stages
 constexpr int TC_STAGE = 128 * 64 * 2;         // bytes per stage: [128 N-rows x 64 K] bf16
 constexpr int TC_XSTAGE = 128 * 16 * 2;        // [128 x 16] bf16 (window-input tiles)
-constexpr int TC_WARP_PROD = 8, TC_WARP_MMA = 9, TC_WARP_AUX = 10;
-constexpr int TC_THREADS = 11 * 32;          // warps 0-7 epilogue, 8 copy producer, 9 MMA issuer, 10 window staging
+constexpr int TC_WARP_AUX0 = 8;               // warps 8-11: window staging (encoder input) / output Linear + error (decoder)
+constexpr int TC_WARP_PROD = 12, TC_WARP_MMA = 13;
+constexpr int TC_THREADS = 16 * 32;          // warps 0-7 epilogue, 8-11 staging/output group, 12 copy producer, 13 MMA issuer, 14-15 idle
 constexpr int TC_EPI_THREADS = 256;
 constexpr float NLOG2E = -1.4426950408889634f;
 
@@ -49,7 +50,7 @@ struct TcDev {
     int n_pass, L;
     unsigned char* scratch;     // per-CTA h_t stream: [grid][T][hi|lo image]
     unsigned long long scratch_stride;
-    int n_tiles_max;
+    long long* dbg;             // optional [grid][8] profiling counters
 };
 
 template <int H>
@@ -59,20 +60,22 @@ struct TcSmem {
     static constexpr int IMG = 2 * IMGH;                    // hi + lo
     static constexpr int off_ring = 0;
     static constexpr int off_in = off_ring + TC_NST * TC_STAGE;
-    static constexpr int off_part = off_in + 2 * IMG;       // xhat partials [2][16][128] fp32
-    static constexpr int off_bias = off_part + 2 * 16 * TCM * 4;
-    static constexpr int off_wo = off_bias + H * 4 * 4;     // [H][16] fp32 + bias[16]
-    static constexpr int off_bar = off_wo + H * 16 * 4 + 64;
+    static constexpr int WOIMG = 16 * H * 2;                // W_o as one fp16 K-major image [16 x H]
+    static constexpr int off_wo = off_in + 2 * IMG;         // hi image, lo image, then b_o[16] fp32
+    static constexpr int off_bias = off_wo + 2 * WOIMG + 64;
+    static constexpr int off_bar = off_bias + H * 4 * 4;
     static constexpr int total = off_bar + 32 * 8 + 16;
     static_assert(total <= 232448, "shared memory budget");
 };
 
 struct TcBars {
-    uint64_t w_full[TC_NST], w_empty[TC_NST], in_full[2], in_empty[2], acc_full[2], acc_empty[2], h_full[2];
+    uint64_t w_full[TC_NST], w_empty[TC_NST], in_full[2], in_empty[2], acc_full[2], acc_empty[2], h_full[2], xhat_full, xhat_empty;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ void aux_bar_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -93,24 +96,46 @@ __device__ __forceinline__ void lstm_cell(float ai, float af, float ag, float ao
     h = (2.f - q) * rcp_approx((1.f + eo) * q);
 }
 
+// optional role profiling (TcDev.dbg != nullptr): cycles the MMA issuer spends in each kind of wait
+#define TC_TWAIT(slot, bar, par)                                   \
+    do {                                                           \
+        const long long _t0 = clock64();                           \
+        mbar_wait(bar, par);                                       \
+        prof[slot] += clock64() - _t0;                             \
+    } while (0)
+
+// mbarrier use-counters: two buffers each; (b ? n1 : n0) keeps them in registers
+struct Cnt2 {
+    uint32_t n0, n1;
+    __device__ __forceinline__ uint32_t get(int b) const { return b ? n1 : n0; }
+    __device__ __forceinline__ void inc(int b) { if (b) ++n1; else ++n0; }
+};
+
+constexpr uint64_t TC_DESC_HI = ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+__device__ __forceinline__ uint64_t kdesc(uint32_t smem_addr) { return TC_DESC_HI | (uint64_t)((smem_addr & 0x3FFFFu) >> 4); }
+
 struct EpiCtx {
     TcBars* bars;
     uint32_t t_acc, hbuf, lane_base;
     const float* bias_s;
-    const float* wo_s;
     unsigned char* img;          // scratch image of this step (SINK_STREAM)
     float* hT;                   // fp32 h_T [H][128] (SINK_LAST_ENC)
-    int wg, row, lane, sink;
+    int wg, row, lane;
     bool last_step;
+    long long* prof;
 };
 
 // One chunk (32 hidden units x 4 gates) of one step for this thread's (row, 16-unit) slice, in two batches of
-// 8 units to bound register pressure: TMEM -> registers, LSTM cell, h_t -> TMEM (bf16 hi|lo) and the pass's sink.
-template <int H, int C>
-__device__ __forceinline__ void epi_chunk(const EpiCtx& x, uint32_t& nacc, float (&cst)[16], float (&xh)[16]) {
+// 8 units to bound register pressure: TMEM -> registers, LSTM cell, h_t -> TMEM (fp16 hi|lo) and the pass's sink.
+template <int H, int C, int SINK>
+__device__ __forceinline__ void epi_chunk(const EpiCtx& x, uint32_t& nacc, float (&cst)[16]) {
     using S = TcSmem<H>;
     constexpr int b = C & 1;
-    mbar_wait(&x.bars->acc_full[b], nacc & 1);
+    {
+        const long long tw0 = clock64();
+        mbar_wait(&x.bars->acc_full[b], nacc & 1);
+        x.prof[C] += clock64() - tw0;
+    }
     ++nacc;
     tc_fence_after_sync();
     const int ub = C * 32 + x.wg * 16;                              // first hidden unit of this thread's slice
@@ -141,27 +166,416 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& x, uint32_t& nacc, float
         for (int j = 0; j < 4; ++j) split_f16x2(hv[2 * j], hv[2 * j + 1], hi[j], lo[j]);
         tmem_st4(x.hbuf + x.lane_base + (uint32_t)(u0 >> 1), hi);
         tmem_st4(x.hbuf + x.lane_base + (uint32_t)(H / 2 + (u0 >> 1)), lo);
-        if (x.sink == SINK_STREAM) {
+        if (SINK == SINK_STREAM) {
             const int off = ((u0 >> 3) * 16 + (x.row >> 3)) * 128 + (x.row & 7) * 16;
             *reinterpret_cast<uint4*>(x.img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4*>(x.img + S::IMGH + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        } else if (x.sink == SINK_LAST_ENC) {
+        } else if (SINK == SINK_LAST_ENC) {
             if (x.last_step) {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) x.hT[(u0 + u) * TCM + x.row] = hv[u];
             }
-        } else {
+        }
+    }
+}
+
+struct PassCtx {
+    TcBars* bars;
+    unsigned char* ring;
+    unsigned char* inbuf;
+    float* bias_s;
+    unsigned char* wo_img;       // W_o fp16 hi|lo K-major images (B operand of the output Linear)
+    float* bo_s;
+    unsigned char* scratch;
+    uint32_t t_acc, t_h;
+    int T, nvalid, hT_buf, u_buf;
+    long long n0;
+};
+
+// ------------------------------------------------------------------------------------------------ epilogue warps
+template <int H, int SINK>
+__device__ __forceinline__ void epi_pass(const PassCtx& pc, const VaeDev& P, const WinSrc& src, const VaeIO& io, const float* bias_g,
+                                      Cnt2 acc_cnt, long long (&prof)[8]) {
+    using S = TcSmem<H>;
+    constexpr int NCH = S::NCH;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wg = warp >> 2;                                  // units [16*wg, 16*wg+16) of each chunk
+    const int row = (warp & 3) * 32 + lane;                    // TMEM lane == window row
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int T = pc.T;
+    for (int i = tid; i < H * 4; i += TC_EPI_THREADS) pc.bias_s[i] = __ldg(bias_g + i);
+    epi_bar_sync();
+    float cst[NCH][16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float4* wv = reinterpret_cast<const float4*>(x.wo_s + (u0 + u) * 16);
-                const float4 w0 = wv[0], w1 = wv[1], w2 = wv[2], w3 = wv[3];
-                xh[0] = fmaf(hv[u], w0.x, xh[0]); xh[1] = fmaf(hv[u], w0.y, xh[1]); xh[2] = fmaf(hv[u], w0.z, xh[2]); xh[3] = fmaf(hv[u], w0.w, xh[3]);
-                xh[4] = fmaf(hv[u], w1.x, xh[4]); xh[5] = fmaf(hv[u], w1.y, xh[5]); xh[6] = fmaf(hv[u], w1.z, xh[6]); xh[7] = fmaf(hv[u], w1.w, xh[7]);
-                xh[8] = fmaf(hv[u], w2.x, xh[8]); xh[9] = fmaf(hv[u], w2.y, xh[9]); xh[10] = fmaf(hv[u], w2.z, xh[10]); xh[11] = fmaf(hv[u], w2.w, xh[11]);
-                xh[12] = fmaf(hv[u], w3.x, xh[12]); xh[13] = fmaf(hv[u], w3.y, xh[13]); xh[14] = fmaf(hv[u], w3.z, xh[14]); xh[15] = fmaf(hv[u], w3.w, xh[15]);
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int u = 0; u < 16; ++u) cst[c][u] = 0.f;
+    uint32_t nacc0 = acc_cnt.n0, nacc1 = acc_cnt.n1;
+    for (int t = 0; t < T; ++t) {
+        const uint32_t hbuf = pc.t_h + (uint32_t)((t & 1) * H);
+        EpiCtx ctx{pc.bars, pc.t_acc, hbuf, lane_base, pc.bias_s, pc.scratch + (size_t)t * S::IMG,
+                   reinterpret_cast<float*>(pc.inbuf + pc.hT_buf * S::IMG), wg, row, lane, t == T - 1, prof};
+        epi_chunk<H, 0, SINK>(ctx, nacc0, cst[0]);
+        if constexpr (NCH > 1) epi_chunk<H, 1, SINK>(ctx, nacc1, cst[1]);
+        if constexpr (NCH > 2) epi_chunk<H, 2, SINK>(ctx, nacc0, cst[2]);
+        if constexpr (NCH > 3) epi_chunk<H, 3, SINK>(ctx, nacc1, cst[3]);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pc.bars->h_full[t & 1]);
+    }
+    if (SINK == SINK_STREAM) fence_proxy_async_all();          // scratch writes -> visible to the bulk-copy engine
+}
+
+// ------------------------------------------------------------------------------------------------ MMA issuer warp
+// One part = accumulate A[128 x K] * W_part^T into a 128-column accumulator.  KIND 0: A = layer input image in
+// shared memory (K = H), 1: A = window tile in shared memory (K = 16, bf16), 2: A = h_{t-1} in TMEM (K = H).
+// Warp-uniform control flow (descriptors live in uniform registers); one elected lane issues.
+template <int H, int KIND>
+__device__ __forceinline__ void mma_part(TcBars* bars, uint32_t ring_a, uint32_t& ring_it, uint32_t acc, uint32_t a_hi,
+                                         uint32_t a_lo, uint32_t first_acc, long long (&prof)[8], bool leader) {
+    constexpr int NKT = (KIND == 1) ? 1 : H / 64;
+    constexpr int KPER = (KIND == 1) ? 1 : 4;
+    constexpr uint32_t IDESC = (KIND == 1) ? make_idesc_bf16(128, 128) : make_idesc_f16(128, 128);
+    uint32_t accf = first_acc;
+#pragma unroll
+    for (int kt = 0; kt < NKT; ++kt) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {           // 0: B_hi stage (A_hi and A_lo), 1: B_lo stage (A_hi)
+            const uint32_t slot = ring_it % TC_NST;
+            TC_TWAIT(0, &bars->w_full[slot], (ring_it / TC_NST) & 1);
+            tc_fence_after_sync();
+            if (leader) {
+                const uint32_t bbase = ring_a + slot * TC_STAGE;
+#pragma unroll
+                for (int j = 0; j < KPER; ++j) {
+                    const int k = kt * KPER + j;           // k-step (16 elements)
+                    const uint64_t bdesc = kdesc(bbase + j * 4096);
+                    if (KIND == 2) {
+                        mma_ts(acc, a_hi + k * 8, bdesc, IDESC, (j == 0) ? accf : 1u);
+                        if (half == 0) mma_ts(acc, a_lo + k * 8, bdesc, IDESC, 1u);
+                    } else {
+                        mma_ss(acc, kdesc(a_hi + k * 4096), bdesc, IDESC, (j == 0) ? accf : 1u);
+                        if (half == 0) mma_ss(acc, kdesc(a_lo + k * 4096), bdesc, IDESC, 1u);
+                    }
+                }
+                mma_commit(&bars->w_empty[slot]);
+            }
+            __syncwarp();
+            accf = 1u;
+            ++ring_it;
+        }
+    }
+}
+
+// xhat = h_t W_o^T : 3-pass fp16 split, M=128 x N=16 x K=H, A = h_t (hi|lo) in TMEM, B = W_o images in smem
+template <int H>
+__device__ __forceinline__ void mma_xhat(TcBars* bars, uint32_t acc, uint32_t h_hi, uint32_t h_lo, uint32_t wo_a, bool leader) {
+    using S = TcSmem<H>;
+    constexpr uint32_t IDESC16 = make_idesc_f16(128, 16);
+    if (leader) {
+#pragma unroll
+        for (int k = 0; k < H / 16; ++k) {
+            const uint64_t bhi = make_smem_desc(wo_a + k * 512, 256, 128);
+            const uint64_t blo = make_smem_desc(wo_a + S::WOIMG + k * 512, 256, 128);
+            mma_ts(acc, h_hi + k * 8, bhi, IDESC16, k > 0 ? 1u : 0u);
+            mma_ts(acc, h_lo + k * 8, bhi, IDESC16, 1u);
+            mma_ts(acc, h_hi + k * 8, blo, IDESC16, 1u);
+        }
+        mma_commit(&bars->xhat_full);
+    }
+    __syncwarp();
+}
+
+template <int H, int IN_KIND, bool LASTDEC>
+__device__ __forceinline__ void mma_pass(const PassCtx& pc, uint32_t ring_it, Cnt2 n_in, Cnt2 n_acc, Cnt2 n_h, uint32_t n_xe,
+                                         long long (&prof)[8]) {
+    using S = TcSmem<H>;
+    constexpr int NCH = S::NCH;
+    constexpr int NFIRST = NCH < 2 ? NCH : 2;
+    constexpr int INK = (IN_KIND == IN_X) ? 1 : 0;
+    static_assert(!LASTDEC || NCH >= 2, "the output Linear borrows accumulator buffer 1");
+    TcBars* bars = pc.bars;
+    const bool leader = (threadIdx.x & 31) == 0;
+    const uint32_t ring_a = smem_u32(pc.ring);
+    const uint32_t in_a = smem_u32(pc.inbuf);
+    const uint32_t wo_a = smem_u32(pc.wo_img);
+    const uint32_t acc1 = pc.t_acc + 128;
+    const int T = pc.T;
+    for (int t = 0; t < T; ++t) {
+        const int tb = t & 1;
+        const bool xh_step = LASTDEC && t > 0;                 // xhat_{t-1} is produced at the head of step t
+        if (IN_KIND != IN_CONST) {
+            TC_TWAIT(1, &bars->in_full[tb], n_in.get(tb) & 1);
+            n_in.inc(tb);
+            tc_fence_after_sync();
+        }
+        uint32_t a_hi, a_lo;
+        if (IN_KIND == IN_X) { a_hi = in_a + tb * 2 * TC_XSTAGE; a_lo = a_hi + TC_XSTAGE; }
+        else { a_hi = in_a + ((IN_KIND == IN_CONST) ? pc.u_buf : tb) * S::IMG; a_lo = a_hi + S::IMGH; }
+        const uint32_t h_hi = pc.t_h + (uint32_t)(((t - 1) & 1) * H), h_lo = h_hi + H / 2;
+        // input projections that do not depend on h_{t-1}: chunk 0 always, chunk 1 unless its accumulator
+        // buffer first has to carry xhat_{t-1}
+#pragma unroll
+        for (int c = 0; c < NFIRST; ++c) {
+            if (c == 1 && xh_step) break;
+            TC_TWAIT(2, &bars->acc_empty[c & 1], (n_acc.get(c & 1) & 1) ^ 1);
+            n_acc.inc(c & 1);
+            tc_fence_after_sync();
+            mma_part<H, INK>(bars, ring_a, ring_it, pc.t_acc + (uint32_t)((c & 1) * 128), a_hi, a_lo, 0u, prof, leader);
+        }
+        if (NCH <= NFIRST && IN_KIND != IN_CONST && !xh_step) { if (leader) mma_commit(&bars->in_empty[tb]); __syncwarp(); }
+        if (t > 0) {
+            TC_TWAIT(3, &bars->h_full[(t - 1) & 1], n_h.get((t - 1) & 1) & 1);
+            n_h.inc((t - 1) & 1);
+            tc_fence_after_sync();
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const uint32_t acc = pc.t_acc + (uint32_t)((c & 1) * 128);
+            if (c == 1 && xh_step) {
+                mbar_wait(&bars->xhat_empty, n_xe & 1);        // output group has read xhat_{t-1}
+                ++n_xe;
+                tc_fence_after_sync();
+                mma_part<H, INK>(bars, ring_a, ring_it, acc, a_hi, a_lo, 0u, prof, leader);
+                if (NCH <= NFIRST && IN_KIND != IN_CONST) { if (leader) mma_commit(&bars->in_empty[tb]); __syncwarp(); }
+            }
+            if (c >= NFIRST) {
+                TC_TWAIT(2, &bars->acc_empty[c & 1], (n_acc.get(c & 1) & 1) ^ 1);
+                n_acc.inc(c & 1);
+                tc_fence_after_sync();
+                mma_part<H, INK>(bars, ring_a, ring_it, acc, a_hi, a_lo, 0u, prof, leader);
+                if (c == NCH - 1 && IN_KIND != IN_CONST) { if (leader) mma_commit(&bars->in_empty[tb]); __syncwarp(); }
+            }
+            if (t > 0) mma_part<H, 2>(bars, ring_a, ring_it, acc, h_hi, h_lo, 1u, prof, leader);
+            if (leader) mma_commit(&bars->acc_full[c & 1]);
+            __syncwarp();
+            if (c == 0 && xh_step) {
+                // off the critical path (chunk 0's recurrent part is already queued): xhat_{t-1} into buffer 1
+                TC_TWAIT(2, &bars->acc_empty[1], (n_acc.get(1) & 1) ^ 1);     // last chunk of step t-1 drained
+                n_acc.inc(1);
+                tc_fence_after_sync();
+                mma_xhat<H>(bars, acc1, h_hi, h_lo, wo_a, leader);
             }
         }
     }
+    // the last step's h_full arrivals are not consumed by a recurrent MMA: consume them here so the phase
+    // bookkeeping stays aligned for the next pass (and xhat_{T-1} needs h_{T-1} anyway)
+    mbar_wait(&bars->h_full[(T - 1) & 1], n_h.get((T - 1) & 1) & 1);
+    if (LASTDEC) {
+        tc_fence_after_sync();
+        mbar_wait(&bars->acc_empty[1], (n_acc.get(1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t h_hi = pc.t_h + (uint32_t)(((T - 1) & 1) * H);
+        mma_xhat<H>(bars, acc1, h_hi, h_hi + H / 2, wo_a, leader);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ copy producer (one lane)
+template <int H>
+__device__ __forceinline__ void prod_pass(const PassCtx& pc, const unsigned char* w, int in_kind, bool lastdec, uint32_t ring_it,
+                                          Cnt2 n_in) {
+    using S = TcSmem<H>;
+    constexpr int NCH = S::NCH;
+    constexpr int NFIRST = NCH < 2 ? NCH : 2;
+    constexpr int KT_PER_PART = H / 64;
+    TcBars* bars = pc.bars;
+    const int T = pc.T;
+    const int part_in_bytes = (in_kind == IN_X) ? 2 * TC_XSTAGE : KT_PER_PART * 2 * TC_STAGE;
+    const int part_hh_bytes = KT_PER_PART * 2 * TC_STAGE;
+    auto load_part = [&](const unsigned char* g, int nstage, uint32_t bytes) {
+        for (int s = 0; s < nstage; ++s) {
+            const uint32_t slot = ring_it % TC_NST;
+            mbar_wait(&bars->w_empty[slot], ((ring_it / TC_NST) & 1) ^ 1);
+            mbar_arrive_expect_tx(&bars->w_full[slot], bytes);
+            bulk_g2s(pc.ring + slot * TC_STAGE, g + (size_t)s * bytes, bytes, &bars->w_full[slot]);
+            ++ring_it;
+        }
+    };
+    auto load_in = [&](int t) {
+        const int b = t & 1;
+        mbar_wait(&bars->in_empty[b], (n_in.get(b) & 1) ^ 1);
+        n_in.inc(b);
+        mbar_arrive_expect_tx(&bars->in_full[b], (uint32_t)S::IMG);
+        const unsigned char* g = pc.scratch + (size_t)t * S::IMG;
+        for (int q = 0; q < S::IMG / 16384; ++q) bulk_g2s(pc.inbuf + b * S::IMG + q * 16384, g + q * 16384, 16384, &bars->in_full[b]);
+    };
+    const int in_nst = (in_kind == IN_X) ? 2 : KT_PER_PART * 2;
+    const uint32_t in_sb = (in_kind == IN_X) ? TC_XSTAGE : TC_STAGE;
+    const size_t chunk_bytes = (size_t)part_in_bytes + part_hh_bytes;
+    if (in_kind == IN_STREAM) load_in(0);
+    for (int t = 0; t < T; ++t) {
+        if (in_kind == IN_STREAM && t + 1 < T) load_in(t + 1);
+        // same order as the MMA issuer: input parts of chunks 0/1 lead, except in the decoder's last layer where
+        // chunk 1's accumulator first carries xhat_{t-1} (its input part then follows chunk 0's recurrent part)
+        const int nlead = (lastdec && t > 0) ? 1 : NFIRST;
+        for (int c = 0; c < nlead; ++c) load_part(w + c * chunk_bytes, in_nst, in_sb);
+        for (int c = 0; c < NCH; ++c) {
+            if (c >= nlead) load_part(w + c * chunk_bytes, in_nst, in_sb);
+            if (t > 0) load_part(w + c * chunk_bytes + part_in_bytes, KT_PER_PART * 2, TC_STAGE);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ staging / output group (warps 8-11)
+// Encoder input: x_t (gather + normalise fused) -> bf16 hi|lo A image [128 x 16]; one window row per thread.
+__device__ __forceinline__ void aux_stage_pass(const PassCtx& pc, const VaeDev& P, const WinSrc& src, const VaeIO& io, Cnt2 n_in,
+                                               long long (&prof)[8]) {
+    TcBars* bars = pc.bars;
+    const int row = threadIdx.x - TC_WARP_AUX0 * 32;
+    const bool ok = row < pc.nvalid;
+    const long long n = pc.n0 + (ok ? row : 0);
+    const long long win = (ok && io.idx) ? (long long)io.idx[n] : n;
+    const float* wbase = src.base + win * src.win_stride;
+    for (int t = 0; t < pc.T; ++t) {
+        const int b = t & 1;
+        float raw[SHM_MAX_D];
+#pragma unroll
+        for (int d = 0; d < SHM_MAX_D; ++d) raw[d] = (ok && d < P.D) ? __ldg(wbase + (long long)t * src.row_stride + src.chan[d]) : 0.f;
+        float v[16];
+#pragma unroll
+        for (int d = 0; d < 16; ++d) v[d] = (ok && d < P.D) ? win_transform_fast(src, raw[d], d) : 0.f;
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+        const long long tw0 = clock64();
+        mbar_wait(&bars->in_empty[b], (n_in.get(b) & 1) ^ 1);
+        prof[0] += clock64() - tw0;
+        n_in.inc(b);
+        unsigned char* xhi = pc.inbuf + b * 2 * TC_XSTAGE;
+        unsigned char* xlo = xhi + TC_XSTAGE;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int off = (q * 16 + (row >> 3)) * 128 + (row & 7) * 16;
+            *reinterpret_cast<uint4*>(xhi + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+            *reinterpret_cast<uint4*>(xlo + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        }
+        fence_proxy_async_smem();
+        aux_bar_sync();
+        if (row == 0) mbar_arrive(&bars->in_full[b]);
+    }
+}
+
+// Decoder output: the MMA warp computes xhat_t = h_t W_o^T on the tensor core (16 spare accumulator columns);
+// this group adds the bias, forms the squared error against the window, optionally stores the
+// reconstruction / CNN input, and writes the per-window score.  One window row per thread.
+__device__ __forceinline__ float ld_nc_volatile(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+template <int H>
+__device__ __forceinline__ void aux_out_pass(const PassCtx& pc, const VaeDev& P, const WinSrc& src, const VaeIO& io, uint32_t n_x,
+                                             long long (&prof)[8]) {
+    TcBars* bars = pc.bars;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = threadIdx.x - TC_WARP_AUX0 * 32;
+    const uint32_t xh_addr = pc.t_acc + 128 + ((uint32_t)((warp & 3) * 32) << 16);      // accumulator buffer 1, columns 0..15
+    const bool ok = row < pc.nvalid;
+    const long long n = pc.n0 + (ok ? row : 0);
+    const long long win = (ok && io.idx) ? (long long)io.idx[n] : n;
+    const float* wbase = src.base + win * src.win_stride;
+    const int T = pc.T;
+    const bool exact = io.cnn_in != nullptr || io.recon != nullptr;     // windows handed back: bit-exact transform
+    float sse = 0.f;
+    for (int t = 0; t < T; ++t) {
+        float x[SHM_MAX_D];                                    // issued before the wait so the latency is hidden
+#pragma unroll
+        for (int d = 0; d < SHM_MAX_D; ++d) x[d] = (ok && d < P.D) ? ld_nc_volatile(wbase + (long long)t * src.row_stride + src.chan[d]) : 0.f;
+        const long long tw0 = clock64();
+        mbar_wait(&bars->xhat_full, n_x & 1);
+        prof[0] += clock64() - tw0;
+        ++n_x;
+        tc_fence_after_sync();
+        uint32_t acc[16];
+        tmem_ld16(xh_addr, acc);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->xhat_empty);
+#pragma unroll
+        for (int d = 0; d < SHM_MAX_D; ++d) {
+            if (d < P.D) {
+                const float y = __uint_as_float(acc[d]) + pc.bo_s[d];
+                const float xv = !ok ? 0.f : (exact ? win_transform(src, x[d], d) : win_transform_fast(src, x[d], d));
+                const float e = xv - y;
+                sse = fmaf(e, e, sse);
+                if (ok) {
+                    if (io.recon) io.recon[(n * T + t) * P.D + d] = y;
+                    if (io.cnn_in) {
+                        io.cnn_in[((n * 2 + 0) * T + t) * P.D + d] = xv;
+                        io.cnn_in[((n * 2 + 1) * T + t) * P.D + d] = e * e;
+                    }
+                }
+            }
+        }
+    }
+    if (ok && io.score) io.score[n] = sse / (float)(T * P.D);
+}
+
+// ------------------------------------------------------------------------------------------------ heads (epilogue warps)
+// LayerNorm -> mu/logvar -> z = mu + eps*exp(0.5 logvar) -> u = tanh(W z + b) as the decoder's constant A operand
+template <int H>
+__device__ __forceinline__ void heads_stage(const PassCtx& pc, const VaeDev& P, const VaeIO& io) {
+    using S = TcSmem<H>;
+    const int tid = threadIdx.x;
+    const int nvalid = pc.nvalid;
+    const long long n0 = pc.n0;
+    float* hT = reinterpret_cast<float*>(pc.inbuf + pc.hT_buf * S::IMG);      // [H][128] fp32
+    float* muS = reinterpret_cast<float*>(pc.ring);                           // [2Z][128]
+    float* zS = muS + 2 * VAE_MAX_Z * TCM;                                    // [Z][128]
+    if (P.has_ln) {
+        if (tid < TCM) {
+            float m = 0.f;
+            for (int k = 0; k < H; ++k) m += hT[k * TCM + tid];
+            m /= (float)H;
+            float v = 0.f;
+            for (int k = 0; k < H; ++k) { const float d = hT[k * TCM + tid] - m; v = fmaf(d, d, v); }
+            v /= (float)H;
+            const float rstd = 1.0f / sqrtf(v + P.ln_eps);
+            for (int k = 0; k < H; ++k)
+                hT[k * TCM + tid] = fmaf((hT[k * TCM + tid] - m) * rstd, __ldg(P.ln_w + k), __ldg(P.ln_b + k));
+        }
+        epi_bar_sync();
+    }
+    for (int item = tid; item < 2 * P.Z * TCM; item += TC_EPI_THREADS) {
+        const int o = item / TCM, w = item - o * TCM;
+        const bool is_lv = o >= P.Z;
+        const int zi = is_lv ? o - P.Z : o;
+        const float* wr = (is_lv ? P.lv_w : P.mu_w) + zi * H;
+        float y = __ldg((is_lv ? P.lv_b : P.mu_b) + zi);
+        for (int k = 0; k < H; ++k) y = fmaf(hT[k * TCM + w], __ldg(wr + k), y);
+        muS[o * TCM + w] = y;
+        if (w < nvalid) {
+            float* dst = is_lv ? io.logvar : io.mu;
+            if (dst) dst[(n0 + w) * P.Z + zi] = y;
+        }
+    }
+    epi_bar_sync();
+    for (int item = tid; item < P.Z * TCM; item += TC_EPI_THREADS) {
+        const int zi = item / TCM, w = item - zi * TCM;
+        const float m = muS[zi * TCM + w], lv = muS[(P.Z + zi) * TCM + w];
+        float z = m;
+        if (io.eps && w < nvalid) z = fmaf(__ldg(io.eps + (n0 + w) * P.Z + zi), expf(0.5f * lv), m);
+        zS[zi * TCM + w] = z;
+    }
+    epi_bar_sync();
+    unsigned short* uhi = reinterpret_cast<unsigned short*>(pc.inbuf + pc.u_buf * S::IMG);
+    unsigned short* ulo = reinterpret_cast<unsigned short*>(pc.inbuf + pc.u_buf * S::IMG + S::IMGH);
+    for (int item = tid; item < H * TCM; item += TC_EPI_THREADS) {
+        const int k = item / TCM, w = item - k * TCM;
+        float y = __ldg(P.l2h_b + k);
+        const float* wr = P.l2h_w + k * P.Z;
+        for (int zi = 0; zi < P.Z; ++zi) y = fmaf(zS[zi * TCM + w], __ldg(wr + zi), y);
+        const float u = tanhf(y);
+        const __half bh = __float2half_rn(u);
+        const __half bl = __float2half_rn(u - __half2float(bh));
+        const int off = ((k >> 3) * 16 + (w >> 3)) * 64 + (w & 7) * 8 + (k & 7);
+        uhi[off] = *reinterpret_cast<const unsigned short*>(&bh);
+        ulo[off] = *reinterpret_cast<const unsigned short*>(&bl);
+    }
+    fence_proxy_async_smem();
 }
 
 template <int H>
@@ -169,19 +583,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
     using S = TcSmem<H>;
     constexpr int NCH = S::NCH;
-    constexpr int NFIRST = NCH < 2 ? NCH : 2;
     constexpr int KT_PER_PART = H / 64;                      // 64-wide K tiles per H-wide part
-    constexpr uint32_t IDESC_H = make_idesc_f16(128, 128);      // fp16 hi|lo operands (h, u, weights)
-    constexpr uint32_t IDESC_X = make_idesc_bf16(128, 128);     // bf16 hi|lo for the raw-window operand (unbounded range)
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* ring = smem + S::off_ring;
-    unsigned char* inbuf = smem + S::off_in;
-    float* part_s = reinterpret_cast<float*>(smem + S::off_part);
-    float* bias_s = reinterpret_cast<float*>(smem + S::off_bias);
-    float* wo_s = reinterpret_cast<float*>(smem + S::off_wo);
-    float* bo_s = wo_s + H * 16;
     TcBars* bars = reinterpret_cast<TcBars*>(smem + S::off_bar);
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + S::off_bar + 32 * 8);
+    unsigned short* wo_hi = reinterpret_cast<unsigned short*>(smem + S::off_wo);
+    unsigned short* wo_lo = wo_hi + 16 * H;
+    float* bo_s = reinterpret_cast<float*>(smem + S::off_wo + 2 * S::WOIMG);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = src.T;
@@ -196,330 +604,120 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
             mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 8);
             mbar_init(&bars->h_full[i], 8);
         }
+        mbar_init(&bars->xhat_full, 1); mbar_init(&bars->xhat_empty, 4);
         fence_mbar_init();
     }
     if (warp == TC_WARP_MMA) tmem_alloc(tmem_holder, 512);
-    for (int i = tid; i < P.D * H; i += TC_THREADS) { const int d = i / H, k = i - d * H; wo_s[k * 16 + d] = __ldg(P.out_w + i); }
+    for (int i = tid; i < 16 * H; i += TC_THREADS) {           // W_o [D,H] -> fp16 hi|lo images, rows d >= D zero
+        const int d = i / H, k = i - d * H;
+        const float w = d < P.D ? __ldg(P.out_w + d * H + k) : 0.f;
+        const __half bh = __float2half_rn(w);
+        const __half bl = __float2half_rn(w - __half2float(bh));
+        const int off = ((k >> 3) * 2 + (d >> 3)) * 64 + (d & 7) * 8 + (k & 7);
+        wo_hi[off] = *reinterpret_cast<const unsigned short*>(&bh);
+        wo_lo[off] = *reinterpret_cast<const unsigned short*>(&bl);
+    }
     if (tid < 16) bo_s[tid] = tid < P.D ? __ldg(P.out_b + tid) : 0.f;
+    fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = *tmem_holder;
-    const uint32_t t_acc = tbase;                 // 2 x 128 accumulator columns
-    const uint32_t t_h = tbase + 256;             // 2 x H columns: h_t as bf16 pairs, [hi H/2 | lo H/2]
 
-    unsigned char* scratch = TC.scratch + (size_t)blockIdx.x * TC.scratch_stride;
-
-    // register budget: the epilogue warpgroups hold the cell state + a full accumulator slice
+    PassCtx pc;
+    pc.bars = bars; pc.ring = smem + S::off_ring; pc.inbuf = smem + S::off_in;
+    pc.bias_s = reinterpret_cast<float*>(smem + S::off_bias);
+    pc.wo_img = smem + S::off_wo; pc.bo_s = bo_s;
+    pc.scratch = TC.scratch + (size_t)blockIdx.x * TC.scratch_stride;
+    pc.t_acc = tbase;                  // 2 x 128 accumulator columns
+    pc.t_h = tbase + 256;              // 2 x H columns: h_t as fp16 pairs, [hi H/2 | lo H/2]
+    pc.T = T;
 
     // Use-counters of the mbarriers.  Every thread carries the same pass-entry values ("base") and
     // advances them analytically at the end of each pass, so roles that skip a barrier in one pass
     // still know its phase in the next; inside a pass each role counts its own uses from the base.
-    uint32_t ring_base = 0, in_base[2] = {0, 0}, acc_base[2] = {0, 0}, h_base[2] = {0, 0};
+    uint32_t ring_base = 0;
+    Cnt2 in_base{0, 0}, acc_base{0, 0}, h_base{0, 0};
+    uint32_t xhat_base = 0;
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long n0 = (long long)tile * TCM;
-        const int nvalid = (int)min((long long)TCM, n_eff - n0);
-        int hT_buf = 1;                            // in-buffer that receives the encoder's fp32 h_T
-        float sse = 0.f;                           // per-row squared error (epilogue warps 0-3)
+    // per-pass bookkeeping shared by both role groups
+    auto pass_setup = [&](int p, int& in_kind, int& sink) {
+        in_kind = TC.pass[p].in_kind; sink = TC.pass[p].sink;
+        if (sink == SINK_LAST_ENC) pc.hT_buf = (in_kind == IN_STREAM) ? (T & 1) : 1;
+        pc.u_buf = pc.hT_buf ^ 1;
+    };
+    auto pass_advance = [&](int in_kind, int sink) {
+        const uint32_t stages_step0 = (uint32_t)NCH * ((in_kind == IN_X) ? 2 : KT_PER_PART * 2);
+        const uint32_t stages_step = stages_step0 + (uint32_t)NCH * KT_PER_PART * 2;
+        ring_base += stages_step0 + (uint32_t)(T - 1) * stages_step;
+        const uint32_t even = (uint32_t)((T + 1) / 2), odd = (uint32_t)(T / 2);
+        if (in_kind != IN_CONST) { in_base.n0 += even; in_base.n1 += odd; }
+        acc_base.n0 += (uint32_t)T * ((NCH + 1) / 2);
+        acc_base.n1 += (uint32_t)T * (NCH / 2);
+        h_base.n0 += even; h_base.n1 += odd;
+        if (sink == SINK_LAST_DEC) xhat_base += (uint32_t)T;
+    };
+    const bool encode_only_call = !io.score && !io.recon && !io.cnn_in;
 
-        for (int p = 0; p < TC.n_pass; ++p) {
-            const TcPassDev ps = TC.pass[p];
-            const int in_kind = ps.in_kind, sink = ps.sink;
-            if (sink == SINK_LAST_ENC) hT_buf = (in_kind == IN_STREAM) ? (T & 1) : 1;
-            const int u_buf = hT_buf ^ 1;
-            const int part_in_bytes = (in_kind == IN_X) ? 2 * TC_XSTAGE : KT_PER_PART * 2 * TC_STAGE;
-            const int part_hh_bytes = KT_PER_PART * 2 * TC_STAGE;
-            uint32_t ring_it = ring_base, n_in[2] = {in_base[0], in_base[1]}, n_acc[2] = {acc_base[0], acc_base[1]},
-                     n_h[2] = {h_base[0], h_base[1]};
-            (void)ring_it; (void)n_in; (void)n_acc; (void)n_h;
-
-            // ------------------------------------------------------------------ heads (between the stacks)
-            if (p == TC.L && warp < 8) {
-                float* hT = reinterpret_cast<float*>(inbuf + hT_buf * S::IMG);      // [H][128] fp32
-                float* muS = reinterpret_cast<float*>(ring);                        // [2Z][128]
-                float* zS = muS + 2 * VAE_MAX_Z * TCM;                              // [Z][128]
-                if (P.has_ln) {
-                    if (tid < TCM) {
-                        float m = 0.f;
-                        for (int k = 0; k < H; ++k) m += hT[k * TCM + tid];
-                        m /= (float)H;
-                        float v = 0.f;
-                        for (int k = 0; k < H; ++k) { const float d = hT[k * TCM + tid] - m; v = fmaf(d, d, v); }
-                        v /= (float)H;
-                        const float rstd = 1.0f / sqrtf(v + P.ln_eps);
-                        for (int k = 0; k < H; ++k)
-                            hT[k * TCM + tid] = fmaf((hT[k * TCM + tid] - m) * rstd, __ldg(P.ln_w + k), __ldg(P.ln_b + k));
-                    }
-                    epi_bar_sync();
-                }
-                for (int item = tid; item < 2 * P.Z * TCM; item += TC_EPI_THREADS) {
-                    const int o = item / TCM, w = item - o * TCM;
-                    const bool is_lv = o >= P.Z;
-                    const int zi = is_lv ? o - P.Z : o;
-                    const float* wr = (is_lv ? P.lv_w : P.mu_w) + zi * H;
-                    float y = __ldg((is_lv ? P.lv_b : P.mu_b) + zi);
-                    for (int k = 0; k < H; ++k) y = fmaf(hT[k * TCM + w], __ldg(wr + k), y);
-                    muS[o * TCM + w] = y;
-                    if (w < nvalid) {
-                        float* dst = is_lv ? io.logvar : io.mu;
-                        if (dst) dst[(n0 + w) * P.Z + zi] = y;
-                    }
-                }
-                epi_bar_sync();
-                for (int item = tid; item < P.Z * TCM; item += TC_EPI_THREADS) {
-                    const int zi = item / TCM, w = item - zi * TCM;
-                    const float m = muS[zi * TCM + w], lv = muS[(P.Z + zi) * TCM + w];
-                    float z = m;
-                    if (io.eps && w < nvalid) z = fmaf(__ldg(io.eps + (n0 + w) * P.Z + zi), expf(0.5f * lv), m);
-                    zS[zi * TCM + w] = z;
-                }
-                epi_bar_sync();
-                // u = tanh(W z + b) as the decoder's constant A operand: bf16 hi|lo K-major images
-                unsigned short* uhi = reinterpret_cast<unsigned short*>(inbuf + u_buf * S::IMG);
-                unsigned short* ulo = reinterpret_cast<unsigned short*>(inbuf + u_buf * S::IMG + S::IMGH);
-                for (int item = tid; item < H * TCM; item += TC_EPI_THREADS) {
-                    const int k = item / TCM, w = item - k * TCM;
-                    float y = __ldg(P.l2h_b + k);
-                    const float* wr = P.l2h_w + k * P.Z;
-                    for (int zi = 0; zi < P.Z; ++zi) y = fmaf(zS[zi * TCM + w], __ldg(wr + zi), y);
-                    const float u = tanhf(y);
-                    const __half bh = __float2half_rn(u);
-                    const __half bl = __float2half_rn(u - __half2float(bh));
-                    const int off = ((k >> 3) * 16 + (w >> 3)) * 64 + (w & 7) * 8 + (k & 7);
-                    uhi[off] = *reinterpret_cast<const unsigned short*>(&bh);
-                    ulo[off] = *reinterpret_cast<const unsigned short*>(&bl);
-                }
-                fence_proxy_async_smem();
-            }
-            const bool encode_only = (p == TC.L) && !io.score && !io.recon && !io.cnn_in;
-            __syncthreads();                       // (A) previous pass / heads complete and visible
-            if (encode_only) break;
-
-            if (warp < 8) {
-                // =============================================================== epilogue warps
-                const int wg = warp >> 2;                                  // units [16*wg, 16*wg+16) of each chunk
-                const int row = (warp & 3) * 32 + lane;                    // TMEM lane == window row
-                const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-                for (int i = tid; i < H * 4; i += TC_EPI_THREADS) bias_s[i] = __ldg(ps.bias + i);
-                epi_bar_sync();
-                float cst[NCH][16];
-#pragma unroll
-                for (int c = 0; c < NCH; ++c)
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) cst[c][u] = 0.f;
-                uint32_t nacc0 = n_acc[0], nacc1 = n_acc[1];
-
-                for (int t = 0; t < T; ++t) {
-                    float xh[16];
-#pragma unroll
-                    for (int d = 0; d < 16; ++d) xh[d] = 0.f;
-                    const uint32_t hbuf = t_h + (uint32_t)((t & 1) * H);
-                    EpiCtx ctx{bars, t_acc, hbuf, lane_base, bias_s, wo_s, scratch + (size_t)t * S::IMG,
-                               reinterpret_cast<float*>(inbuf + hT_buf * S::IMG), wg, row, lane, sink, t == T - 1};
-                    epi_chunk<H, 0>(ctx, nacc0, cst[0], xh);
-                    if constexpr (NCH > 1) epi_chunk<H, 1>(ctx, nacc1, cst[1], xh);
-                    if constexpr (NCH > 2) epi_chunk<H, 2>(ctx, nacc0, cst[2], xh);
-                    if constexpr (NCH > 3) epi_chunk<H, 3>(ctx, nacc1, cst[3], xh);
-                    tmem_st_wait();
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->h_full[t & 1]);
-
-                    if (sink == SINK_LAST_DEC) {
-                        // xhat_t = W_o h_t + b_o : combine the two unit halves, then the squared error of this row
-                        float* ps_ = part_s + (t & 1) * 16 * TCM;
-                        if (wg == 1) {
-#pragma unroll
-                            for (int d = 0; d < 16; ++d) ps_[d * TCM + row] = xh[d];
-                        }
-                        epi_bar_sync();
-                        if (wg == 0) {
-                            const bool valid = row < nvalid;
-                            const long long n = n0 + row;
-                            const long long win = (valid && io.idx) ? (long long)io.idx[n] : n;
-                            for (int d = 0; d < P.D; ++d) {
-                                const float y = xh[d] + ps_[d * TCM + row] + bo_s[d];
-                                const float x = valid ? win_fetch(src, win, t, d) : 0.f;
-                                const float e = x - y;
-                                sse = fmaf(e, e, sse);
-                                if (valid) {
-                                    if (io.recon) io.recon[(n * T + t) * P.D + d] = y;
-                                    if (io.cnn_in) {
-                                        io.cnn_in[((n * 2 + 0) * T + t) * P.D + d] = x;
-                                        io.cnn_in[((n * 2 + 1) * T + t) * P.D + d] = e * e;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-                if (sink == SINK_STREAM) fence_proxy_async_all();          // scratch writes -> visible to the bulk-copy engine
-                if (sink == SINK_LAST_DEC && wg == 0 && row < nvalid && io.score) io.score[n0 + row] = sse / (float)(T * P.D);
-            } else if (warp == TC_WARP_PROD) {
-                // =============================================================== copy producer (one lane)
-                if (lane == 0) {
-                    auto load_stage = [&](const unsigned char* g, uint32_t bytes) {
-                        const uint32_t slot = ring_it % TC_NST;
-                        mbar_wait(&bars->w_empty[slot], ((ring_it / TC_NST) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&bars->w_full[slot], bytes);
-                        bulk_g2s(ring + slot * TC_STAGE, g, bytes, &bars->w_full[slot]);
-                        ++ring_it;
-                    };
-                    auto load_part = [&](const unsigned char* g, int nstage, uint32_t bytes) {
-                        for (int s = 0; s < nstage; ++s) load_stage(g + (size_t)s * bytes, bytes);
-                    };
-                    auto load_in = [&](int t) {
-                        const int b = t & 1;
-                        mbar_wait(&bars->in_empty[b], (n_in[b] & 1) ^ 1);
-                        ++n_in[b];
-                        mbar_arrive_expect_tx(&bars->in_full[b], (uint32_t)S::IMG);
-                        const unsigned char* g = scratch + (size_t)t * S::IMG;
-                        for (int q = 0; q < S::IMG / 16384; ++q)
-                            bulk_g2s(inbuf + b * S::IMG + q * 16384, g + q * 16384, 16384, &bars->in_full[b]);
-                    };
-                    const int in_nst = (in_kind == IN_X) ? 2 : KT_PER_PART * 2;
-                    const uint32_t in_sb = (in_kind == IN_X) ? TC_XSTAGE : TC_STAGE;
-                    const size_t chunk_bytes = (size_t)part_in_bytes + part_hh_bytes;
-                    if (in_kind == IN_STREAM) load_in(0);
-                    for (int t = 0; t < T; ++t) {
-                        if (in_kind == IN_STREAM && t + 1 < T) load_in(t + 1);
-                        for (int c = 0; c < NFIRST; ++c) load_part(ps.w + c * chunk_bytes, in_nst, in_sb);
-                        for (int c = 0; c < NCH; ++c) {
-                            if (c >= NFIRST) load_part(ps.w + c * chunk_bytes, in_nst, in_sb);
-                            if (t > 0) load_part(ps.w + c * chunk_bytes + part_in_bytes, KT_PER_PART * 2, TC_STAGE);
-                        }
-                    }
-                }
-            } else if (warp == TC_WARP_MMA) {
-                // =============================================================== MMA issuer (one lane)
-                if (lane == 0) {
-                    const uint32_t ring_a = smem_u32(ring);
-                    // one part = accumulate  A[128 x K] * W_part^T  into acc: A from smem (layer input) or TMEM (h_{t-1})
-                    auto do_part = [&](bool is_in, int c, int t, uint32_t first_acc) {
-                        const uint32_t acc = t_acc + (uint32_t)((c & 1) * 128);
-                        const bool xin = is_in && in_kind == IN_X;
-                        const int kper = xin ? 1 : 4;
-                        const int nkt = xin ? 1 : KT_PER_PART;
-                        uint32_t a_hi_s = 0, a_lo_s = 0, a_hi_t = 0, a_lo_t = 0;
-                        if (is_in) {
-                            if (xin) { a_hi_s = smem_u32(inbuf) + (t & 1) * 2 * TC_XSTAGE; a_lo_s = a_hi_s + TC_XSTAGE; }
-                            else {
-                                const int b = (in_kind == IN_CONST) ? u_buf : (t & 1);
-                                a_hi_s = smem_u32(inbuf) + b * S::IMG; a_lo_s = a_hi_s + S::IMGH;
-                            }
-                        } else {
-                            a_hi_t = t_h + (uint32_t)(((t - 1) & 1) * H); a_lo_t = a_hi_t + H / 2;
-                        }
-                        uint32_t accf = first_acc;
-                        const uint32_t IDESC = xin ? IDESC_X : IDESC_H;
-                        for (int kt = 0; kt < nkt; ++kt) {
-#pragma unroll
-                            for (int half = 0; half < 2; ++half) {           // 0: B_hi stage (A_hi and A_lo), 1: B_lo stage (A_hi)
-                                const uint32_t slot = ring_it % TC_NST;
-                                mbar_wait(&bars->w_full[slot], (ring_it / TC_NST) & 1);
-                                tc_fence_after_sync();
-                                for (int j = 0; j < kper; ++j) {
-                                    const int k = kt * kper + j;               // k-step (16 elements)
-                                    const uint64_t bdesc = make_smem_desc(ring_a + slot * TC_STAGE + j * 4096, 2048, 128);
-                                    if (is_in) {
-                                        mma_ss(acc, make_smem_desc(a_hi_s + k * 4096, 2048, 128), bdesc, IDESC, accf);
-                                        accf = 1;
-                                        if (half == 0) mma_ss(acc, make_smem_desc(a_lo_s + k * 4096, 2048, 128), bdesc, IDESC, 1);
-                                    } else {
-                                        mma_ts(acc, a_hi_t + k * 8, bdesc, IDESC, accf);
-                                        accf = 1;
-                                        if (half == 0) mma_ts(acc, a_lo_t + k * 8, bdesc, IDESC, 1);
-                                    }
-                                }
-                                mma_commit(&bars->w_empty[slot]);
-                                ++ring_it;
-                            }
-                        }
-                    };
-                    for (int t = 0; t < T; ++t) {
-                        if (in_kind != IN_CONST) {
-                            mbar_wait(&bars->in_full[t & 1], n_in[t & 1] & 1);
-                            ++n_in[t & 1];
-                            tc_fence_after_sync();
-                        }
-                        for (int c = 0; c < NFIRST; ++c) {
-                            mbar_wait(&bars->acc_empty[c & 1], (n_acc[c & 1] & 1) ^ 1);
-                            ++n_acc[c & 1];
-                            tc_fence_after_sync();
-                            do_part(true, c, t, 0);
-                        }
-                        if (NCH <= NFIRST && in_kind != IN_CONST) mma_commit(&bars->in_empty[t & 1]);
-                        if (t > 0) {
-                            mbar_wait(&bars->h_full[(t - 1) & 1], n_h[(t - 1) & 1] & 1);
-                            ++n_h[(t - 1) & 1];
-                            tc_fence_after_sync();
-                        }
-                        for (int c = 0; c < NCH; ++c) {
-                            if (c >= NFIRST) {
-                                mbar_wait(&bars->acc_empty[c & 1], (n_acc[c & 1] & 1) ^ 1);
-                                ++n_acc[c & 1];
-                                tc_fence_after_sync();
-                                do_part(true, c, t, 0);
-                                if (c == NCH - 1 && in_kind != IN_CONST) mma_commit(&bars->in_empty[t & 1]);
-                            }
-                            if (t > 0) do_part(false, c, t, 1);
-                            mma_commit(&bars->acc_full[c & 1]);
-                        }
-                    }
-                    // the last step's h_full arrivals are never consumed by an MMA: consume them here so the
-                    // phase bookkeeping stays aligned for the next pass
-                    mbar_wait(&bars->h_full[(T - 1) & 1], n_h[(T - 1) & 1] & 1);
-                    ++n_h[(T - 1) & 1];
-                }
-            } else if (warp == TC_WARP_AUX) {
-                // =============================================================== window staging: x_t -> bf16 hi|lo A image
-                if (in_kind == IN_X) {
-                    for (int t = 0; t < T; ++t) {
-                        const int b = t & 1;
-                        mbar_wait(&bars->in_empty[b], (n_in[b] & 1) ^ 1);
-                        ++n_in[b];
-                        unsigned char* xhi = inbuf + b * 2 * TC_XSTAGE;
-                        unsigned char* xlo = xhi + TC_XSTAGE;
-#pragma unroll
-                        for (int rr = 0; rr < 4; ++rr) {
-                            const int row = rr * 32 + lane;
-                            float v[16];
-#pragma unroll
-                            for (int d = 0; d < 16; ++d) v[d] = 0.f;
-                            if (row < nvalid) {
-                                const long long n = n0 + row;
-                                const long long win = io.idx ? (long long)io.idx[n] : n;
-                                for (int d = 0; d < P.D; ++d) v[d] = win_fetch(src, win, t, d);
-                            }
-                            uint32_t hi[8], lo[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-#pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                const int off = (q * 16 + (row >> 3)) * 128 + (row & 7) * 16;
-                                *reinterpret_cast<uint4*>(xhi + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-                                *reinterpret_cast<uint4*>(xlo + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-                            }
-                        }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars->in_full[b]);
-                    }
-                }
-            }
-            __syncthreads();                       // (B) end of pass
-            {
-                const uint32_t stages_step0 = (uint32_t)NCH * ((in_kind == IN_X) ? 2 : KT_PER_PART * 2);
-                const uint32_t stages_step = stages_step0 + (uint32_t)NCH * KT_PER_PART * 2;
-                ring_base += stages_step0 + (uint32_t)(T - 1) * stages_step;
-                const uint32_t even = (uint32_t)((T + 1) / 2), odd = (uint32_t)(T / 2);
-                if (in_kind != IN_CONST) { in_base[0] += even; in_base[1] += odd; }
-                acc_base[0] += (uint32_t)T * ((NCH + 1) / 2);
-                acc_base[1] += (uint32_t)T * (NCH / 2);
-                h_base[0] += even; h_base[1] += odd;
+    // Role groups at top level so that each group's code is dominated by its setmaxnreg: the two epilogue
+    // warpgroups take 208 registers per thread (cell state + accumulator slices + deep ILP), the
+    // producer / MMA / staging warpgroup drops to 88.  CTA-wide phases meet at barrier 0.
+    if (warp < 8) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            pc.n0 = (long long)tile * TCM;
+            pc.nvalid = (int)min((long long)TCM, n_eff - pc.n0);
+            pc.hT_buf = 1;                         // in-buffer that receives the encoder's fp32 h_T
+            for (int p = 0; p < TC.n_pass; ++p) {
+                int in_kind, sink;
+                pass_setup(p, in_kind, sink);
+                if (p == TC.L) heads_stage<H>(pc, P, io);
+                cta_sync();                        // (A) previous pass / heads complete and visible
+                if (p == TC.L && encode_only_call) break;
+                const long long pass_t0 = clock64();
+                if (sink == SINK_STREAM) epi_pass<H, SINK_STREAM>(pc, P, src, io, TC.pass[p].bias, acc_base, prof);
+                else if (sink == SINK_LAST_ENC) epi_pass<H, SINK_LAST_ENC>(pc, P, src, io, TC.pass[p].bias, acc_base, prof);
+                else epi_pass<H, SINK_LAST_DEC>(pc, P, src, io, TC.pass[p].bias, acc_base, prof);
+                prof[4 + (p & 3)] += clock64() - pass_t0;
+                cta_sync();                        // (B) end of pass
+                pass_advance(in_kind, sink);
             }
         }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            pc.n0 = (long long)tile * TCM;
+            pc.nvalid = (int)min((long long)TCM, n_eff - pc.n0);
+            pc.hT_buf = 1;
+            for (int p = 0; p < TC.n_pass; ++p) {
+                int in_kind, sink;
+                pass_setup(p, in_kind, sink);
+                cta_sync();                        // (A)
+                if (p == TC.L && encode_only_call) break;
+                if (warp == TC_WARP_PROD) {
+                    if (lane == 0) prod_pass<H>(pc, TC.pass[p].w, in_kind, sink == SINK_LAST_DEC, ring_base, in_base);
+                } else if (warp == TC_WARP_MMA) {
+                    const long long pass_t0 = clock64();
+                    if (sink == SINK_LAST_DEC) {
+                        if (in_kind == IN_STREAM) mma_pass<H, IN_STREAM, true>(pc, ring_base, in_base, acc_base, h_base, xhat_base, prof);
+                        else mma_pass<H, IN_CONST, true>(pc, ring_base, in_base, acc_base, h_base, xhat_base, prof);
+                    } else if (in_kind == IN_X) mma_pass<H, IN_X, false>(pc, ring_base, in_base, acc_base, h_base, xhat_base, prof);
+                    else if (in_kind == IN_STREAM) mma_pass<H, IN_STREAM, false>(pc, ring_base, in_base, acc_base, h_base, xhat_base, prof);
+                    else mma_pass<H, IN_CONST, false>(pc, ring_base, in_base, acc_base, h_base, xhat_base, prof);
+                    prof[4 + (p & 3)] += clock64() - pass_t0;
+                } else if (warp >= TC_WARP_AUX0 && warp < TC_WARP_AUX0 + 4) {
+                    if (in_kind == IN_X) aux_stage_pass(pc, P, src, io, in_base, prof);
+                    if (sink == SINK_LAST_DEC) aux_out_pass<H>(pc, P, src, io, xhat_base, prof);
+                }
+                cta_sync();                        // (B)
+                pass_advance(in_kind, sink);
+            }
+        }
+    }
+    if (TC.dbg && lane == 0 && (warp == TC_WARP_MMA || warp == TC_WARP_AUX0 || warp == 0)) {
+        const int role = (warp == TC_WARP_MMA) ? 0 : (warp == TC_WARP_AUX0 ? 1 : 2);
+        for (int i = 0; i < 8; ++i) TC.dbg[(blockIdx.x * 3 + role) * 8 + i] = prof[i];
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -632,6 +830,8 @@ void vae_tc_free(VaeTc* tc) {
     if (tc->wpack) cudaFree(tc->wpack);
     if (tc->bias) cudaFree(tc->bias);
     if (tc->scratch) cudaFree(tc->scratch);
+    if (tc->dbg) cudaFree(tc->dbg);
+    tc->dbg = nullptr;
     tc->wpack = nullptr; tc->bias = nullptr; tc->scratch = nullptr;
 }
 
@@ -655,6 +855,7 @@ int vae_tc_score(VaeTc* tc, const VaeDev& P, const WinSrc& src, const VaeIO& io,
     memset(&T, 0, sizeof(T));
     T.n_pass = 2 * L; T.L = L;
     T.scratch = static_cast<unsigned char*>(tc->scratch); T.scratch_stride = stride;
+    T.dbg = tc->dbg;
     for (int p = 0; p < 2 * L; ++p) {
         const bool dec = p >= L;
         const int l = dec ? p - L : p;

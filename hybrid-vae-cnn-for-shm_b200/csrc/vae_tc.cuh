@@ -17,6 +17,7 @@ struct VaeTc {
     size_t wpack_bytes, scratch_bytes;
     size_t pass_off[2 * SHM_MAX_L];
     int H, L, D;
+    long long* dbg;    // optional profiling counters [#SM][8] (shm_vae_debug_counters)
 };
 
 bool vae_tc_supported(const shm_vae_cfg& cfg);

@@ -65,6 +65,7 @@ SIGNATURES = {
     "shm_vae_update_weights": (C.c_int, [_vp, C.POINTER(VaeWeights), _vp]),
     "shm_vae_destroy": (C.c_int, [_vp]),
     "shm_vae_engine": (C.c_int, [_vp]),
+    "shm_vae_debug_counters": (C.c_int, [_vp, _vp, C.c_int]),
     "shm_vae_score": (C.c_int, [_vp, C.POINTER(WindowSrc), _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "shm_vae_decode": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, _vp]),
     "shm_compact_workspace_bytes": (C.c_int64, [C.c_int64]),

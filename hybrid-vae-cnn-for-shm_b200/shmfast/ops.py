@@ -202,6 +202,12 @@ class VaeScorer:
                                           _ptr(mu), _ptr(lv), _ptr(recon), _ptr(cnn_in), _stream()), "shm_vae_score")
         return out
 
+    def debug_counters(self, n_cta: int = 148):
+        """Tensor-core engine profiling counters [n_cta, 8] (first call enables them)."""
+        buf = np.zeros((n_cta, 3, 8), dtype=np.int64)     # roles: MMA issuer, window-staging warp, epilogue warp 0
+        check(self._lib.shm_vae_debug_counters(self._h, buf.ctypes.data_as(C.c_void_p), buf.size), "shm_vae_debug_counters")
+        return buf
+
     def decode(self, z: torch.Tensor, T: int) -> torch.Tensor:
         """TemporalVAE.decode (temporal_vae.py:65-70): z [n,Z] -> recon [n,T,D]."""
         z = _f32c(z, "z")

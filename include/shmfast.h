@@ -128,6 +128,10 @@ int shm_vae_create(shm_vae** out, const shm_vae_cfg* cfg_host, const shm_vae_wei
 int shm_vae_update_weights(shm_vae* h, const shm_vae_weights* w_host, void* stream);
 int shm_vae_destroy(shm_vae* h);
 int shm_vae_engine(const shm_vae* h);    /* the engine actually selected */
+/* Profiling aid (tensor-core engine): the first call enables per-CTA cycle counters of the MMA-issuer warp,
+ * later calls copy them out: out_host[cta*8 + {0: wait weights, 1: wait input, 2: wait accumulator drain,
+ * 3: wait h_t, 4..7: total cycles of pass 0..3}], accumulated over launches. */
+int shm_vae_debug_counters(shm_vae* h, long long* out_host, int n);
 
 /* Fused forward + score for n windows: encode -> z = mu + eps*exp(0.5*logvar) -> decode ->
  * score[n] = mean_{t,d} (x - xhat)^2.  Replaces TemporalVAE.forward (temporal_vae.py:72-77) and the
