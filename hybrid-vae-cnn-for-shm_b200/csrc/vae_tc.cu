@@ -28,7 +28,7 @@ namespace shm {
 using namespace tc;
 
 constexpr int TCM = 128;                       // windows per tile (UMMA M)
-constexpr int TC_NST = 4;                      // weight ring stages
+constexpr int TC_NST = 5;                      // weight ring stages
 constexpr int TC_STAGE = 128 * 64 * 2;         // bytes per stage: [128 N-rows x 64 K] bf16
 constexpr int TC_XSTAGE = 128 * 16 * 2;        // [128 x 16] bf16 (window-input tiles)
 constexpr int TC_WARP_AUX0 = 8;               // warps 8-11: window staging (encoder input) / output Linear + error (decoder)
@@ -134,7 +134,7 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& x, uint32_t& nacc, float
     {
         const long long tw0 = clock64();
         mbar_wait(&x.bars->acc_full[b], nacc & 1);
-        x.prof[C] += clock64() - tw0;
+        x.prof[C < 3 ? C : 2] += clock64() - tw0;
     }
     ++nacc;
     tc_fence_after_sync();
@@ -147,7 +147,11 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& x, uint32_t& nacc, float
         tmem_ld8(abase + 32, g1);
         tmem_ld8(abase + 64, g2);
         tmem_ld8(abase + 96, g3);
-        tmem_ld_wait();
+        {
+            const long long tl0 = clock64();
+            tmem_ld_wait();
+            if (C == 3) x.prof[3] += clock64() - tl0; else x.prof[3] += clock64() - tl0;
+        }
         if (half == 1) {                                             // accumulator slice fully in registers: release it
             tc_fence_before_sync();
             __syncwarp();
@@ -245,7 +249,7 @@ __device__ __forceinline__ void mma_part(TcBars* bars, uint32_t ring_a, uint32_t
             const uint32_t slot = ring_it % TC_NST;
             TC_TWAIT(0, &bars->w_full[slot], (ring_it / TC_NST) & 1);
             tc_fence_after_sync();
-            if (leader) {
+            if (elect_one()) {
                 const uint32_t bbase = ring_a + slot * TC_STAGE;
 #pragma unroll
                 for (int j = 0; j < KPER; ++j) {
@@ -273,7 +277,7 @@ template <int H>
 __device__ __forceinline__ void mma_xhat(TcBars* bars, uint32_t acc, uint32_t h_hi, uint32_t h_lo, uint32_t wo_a, bool leader) {
     using S = TcSmem<H>;
     constexpr uint32_t IDESC16 = make_idesc_f16(128, 16);
-    if (leader) {
+    if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < H / 16; ++k) {
             const uint64_t bhi = make_smem_desc(wo_a + k * 512, 256, 128);
@@ -297,11 +301,16 @@ __device__ __forceinline__ void mma_pass(const PassCtx& pc, uint32_t ring_it, Cn
     static_assert(!LASTDEC || NCH >= 2, "the output Linear borrows accumulator buffer 1");
     TcBars* bars = pc.bars;
     const bool leader = (threadIdx.x & 31) == 0;
-    const uint32_t ring_a = smem_u32(pc.ring);
-    const uint32_t in_a = smem_u32(pc.inbuf);
-    const uint32_t wo_a = smem_u32(pc.wo_img);
-    const uint32_t acc1 = pc.t_acc + 128;
-    const int T = pc.T;
+    // warp-uniform by construction; the shuffles let the compiler keep descriptors in uniform registers
+    const uint32_t ring_a = __shfl_sync(0xffffffffu, smem_u32(pc.ring), 0);
+    const uint32_t in_a = __shfl_sync(0xffffffffu, smem_u32(pc.inbuf), 0);
+    const uint32_t wo_a = __shfl_sync(0xffffffffu, smem_u32(pc.wo_img), 0);
+    const uint32_t t_acc = __shfl_sync(0xffffffffu, pc.t_acc, 0);
+    const uint32_t t_h = __shfl_sync(0xffffffffu, pc.t_h, 0);
+    const int u_buf = __shfl_sync(0xffffffffu, pc.u_buf, 0);
+    ring_it = __shfl_sync(0xffffffffu, ring_it, 0);
+    const uint32_t acc1 = t_acc + 128;
+    const int T = __shfl_sync(0xffffffffu, pc.T, 0);
     for (int t = 0; t < T; ++t) {
         const int tb = t & 1;
         const bool xh_step = LASTDEC && t > 0;                 // xhat_{t-1} is produced at the head of step t
@@ -312,8 +321,8 @@ __device__ __forceinline__ void mma_pass(const PassCtx& pc, uint32_t ring_it, Cn
         }
         uint32_t a_hi, a_lo;
         if (IN_KIND == IN_X) { a_hi = in_a + tb * 2 * TC_XSTAGE; a_lo = a_hi + TC_XSTAGE; }
-        else { a_hi = in_a + ((IN_KIND == IN_CONST) ? pc.u_buf : tb) * S::IMG; a_lo = a_hi + S::IMGH; }
-        const uint32_t h_hi = pc.t_h + (uint32_t)(((t - 1) & 1) * H), h_lo = h_hi + H / 2;
+        else { a_hi = in_a + ((IN_KIND == IN_CONST) ? u_buf : tb) * S::IMG; a_lo = a_hi + S::IMGH; }
+        const uint32_t h_hi = t_h + (uint32_t)(((t - 1) & 1) * H), h_lo = h_hi + H / 2;
         // input projections that do not depend on h_{t-1}: chunk 0 always, chunk 1 unless its accumulator
         // buffer first has to carry xhat_{t-1}
 #pragma unroll
@@ -322,9 +331,9 @@ __device__ __forceinline__ void mma_pass(const PassCtx& pc, uint32_t ring_it, Cn
             TC_TWAIT(2, &bars->acc_empty[c & 1], (n_acc.get(c & 1) & 1) ^ 1);
             n_acc.inc(c & 1);
             tc_fence_after_sync();
-            mma_part<H, INK>(bars, ring_a, ring_it, pc.t_acc + (uint32_t)((c & 1) * 128), a_hi, a_lo, 0u, prof, leader);
+            mma_part<H, INK>(bars, ring_a, ring_it, t_acc + (uint32_t)((c & 1) * 128), a_hi, a_lo, 0u, prof, leader);
         }
-        if (NCH <= NFIRST && IN_KIND != IN_CONST && !xh_step) { if (leader) mma_commit(&bars->in_empty[tb]); __syncwarp(); }
+        if (NCH <= NFIRST && IN_KIND != IN_CONST && !xh_step) { if (elect_one()) mma_commit(&bars->in_empty[tb]); __syncwarp(); }
         if (t > 0) {
             TC_TWAIT(3, &bars->h_full[(t - 1) & 1], n_h.get((t - 1) & 1) & 1);
             n_h.inc((t - 1) & 1);
@@ -332,23 +341,23 @@ __device__ __forceinline__ void mma_pass(const PassCtx& pc, uint32_t ring_it, Cn
         }
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-            const uint32_t acc = pc.t_acc + (uint32_t)((c & 1) * 128);
+            const uint32_t acc = t_acc + (uint32_t)((c & 1) * 128);
             if (c == 1 && xh_step) {
                 mbar_wait(&bars->xhat_empty, n_xe & 1);        // output group has read xhat_{t-1}
                 ++n_xe;
                 tc_fence_after_sync();
                 mma_part<H, INK>(bars, ring_a, ring_it, acc, a_hi, a_lo, 0u, prof, leader);
-                if (NCH <= NFIRST && IN_KIND != IN_CONST) { if (leader) mma_commit(&bars->in_empty[tb]); __syncwarp(); }
+                if (NCH <= NFIRST && IN_KIND != IN_CONST) { if (elect_one()) mma_commit(&bars->in_empty[tb]); __syncwarp(); }
             }
             if (c >= NFIRST) {
                 TC_TWAIT(2, &bars->acc_empty[c & 1], (n_acc.get(c & 1) & 1) ^ 1);
                 n_acc.inc(c & 1);
                 tc_fence_after_sync();
                 mma_part<H, INK>(bars, ring_a, ring_it, acc, a_hi, a_lo, 0u, prof, leader);
-                if (c == NCH - 1 && IN_KIND != IN_CONST) { if (leader) mma_commit(&bars->in_empty[tb]); __syncwarp(); }
+                if (c == NCH - 1 && IN_KIND != IN_CONST) { if (elect_one()) mma_commit(&bars->in_empty[tb]); __syncwarp(); }
             }
             if (t > 0) mma_part<H, 2>(bars, ring_a, ring_it, acc, h_hi, h_lo, 1u, prof, leader);
-            if (leader) mma_commit(&bars->acc_full[c & 1]);
+            if (elect_one()) mma_commit(&bars->acc_full[c & 1]);
             __syncwarp();
             if (c == 0 && xh_step) {
                 // off the critical path (chunk 0's recurrent part is already queued): xhat_{t-1} into buffer 1
@@ -366,7 +375,7 @@ __device__ __forceinline__ void mma_pass(const PassCtx& pc, uint32_t ring_it, Cn
         tc_fence_after_sync();
         mbar_wait(&bars->acc_empty[1], (n_acc.get(1) & 1) ^ 1);
         tc_fence_after_sync();
-        const uint32_t h_hi = pc.t_h + (uint32_t)(((T - 1) & 1) * H);
+        const uint32_t h_hi = t_h + (uint32_t)(((T - 1) & 1) * H);
         mma_xhat<H>(bars, acc1, h_hi, h_hi + H / 2, wo_a, leader);
     }
 }

@@ -17,4 +17,4 @@ print(f"N={N} {ms:.2f} ms -> {N/ms*1e3/1e6:.3f} M windows/s")
 m = c.mean(0) / 1e6
 print("MMA issuer : wait weights %.2f  input %.2f  acc drain %.2f  h %.2f | pass totals %s" % (m[0,0], m[0,1], m[0,2], m[0,3], np.round(m[0,4:], 2)))
 print("aux warp 8 : wait (in_empty / xhat_full) %.2f" % (m[1,0],))
-print("epilogue w0: wait acc_full per chunk %s | pass totals %s" % (np.round(m[2,:4], 2), np.round(m[2,4:], 2)))
+print("epilogue w0: wait acc_full c0,c1,c2+3, tmem-ld %s | pass totals %s" % (np.round(m[2,:4], 2), np.round(m[2,4:], 2)))
