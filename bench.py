@@ -51,7 +51,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["shmfast", "reference"], default="shmfast")
-    ap.add_argument("--workload", choices=["4dof_hybrid", "4dof_score"], default="4dof_hybrid")
+    ap.add_argument("--workload", choices=["4dof_hybrid", "4dof_score", "openlab_hybrid"], default="4dof_hybrid")
+    ap.add_argument("--flag-pct", type=float, default=None, help="openlab_hybrid: percentile used as gate threshold (default 95)")
     ap.add_argument("--windows", type=int, default=1 << 20, help="windows per GPU per step")
     ap.add_argument("--engine", choices=["auto", "fp32", "tc"], default="auto")
     ap.add_argument("--cpu-sample", type=int, default=16384, help="windows per CPU-baseline sample")
@@ -330,9 +331,173 @@ def run_shmfast(a):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------
+# openLAB hybrid (BASELINE.json configs[3] per GPU): gate on 3 clean channels (T=200, stride 20), CNN on the
+# flagged raw 4-channel windows; thresholds P95 (default) of a 2,000-window calibration sample and 0.5.
+# ----------------------------------------------------------------------------------------------
+def openlab_problem(n_windows: int, seed: int):
+    from shmfast import synth
+    rows = (n_windows - 1) * 20 + 200
+    series = synth.series(rows, 4, seed=seed, nan_frac=0.0007)          # ~1.35 % of the raw windows carry a NaN run
+    vmu, vsd = synth.stats(3, seed=1)
+    cmu, csd = synth.stats(4, seed=2)
+    return series, vmu, vsd, cmu, csd
+
+
+def run_openlab(a):
+    import torch.distributed as dist
+
+    from shmfast import ops, synth
+    from shmfast.pipeline import HybridOpenLab
+    from shmfast.shard import max_over_ranks, sum_over_ranks
+
+    pct = 95.0 if a.flag_pct is None else a.flag_pct
+    if a.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        from oracle import torch_port as TP
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        n = min(a.cpu_sample, a.windows)
+        series, vmu, vsd, cmu, csd = openlab_problem(n, seed=123)
+        vae = TP.VaePort(synth.stage_vae_weights("openlab", seed=0))
+        cnn = TP.CnnOpenLabPort(synth.cnnol_weights(seed=0))
+        torch.manual_seed(42)
+        cal = TP.hybrid_openlab(vae, cnn, series[: (min(2000, n) - 1) * 20 + 200], [1, 2, 3], vmu, vsd, cmu, csd, float("inf"), 0.5)
+        thr = float(np.percentile(cal["score"], pct))
+        times = []
+        for i in range(a.warmup + a.steps):
+            t0 = time.perf_counter()
+            r = TP.hybrid_openlab(vae, cnn, series, [1, 2, 3], vmu, vsd, cmu, csd, thr, 0.5)
+            if i >= a.warmup:
+                times.append(time.perf_counter() - t0)
+        ms = 1e3 * sum(times) / len(times)
+        val = n / (ms / 1e3)
+        sample = f"{n} windows of the openlab_hybrid step per timed pass (torch.nn CPU kernels, batch 256), flagged {int(r['mask'].sum())}"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "windows/s", "n_gpus": a.gpus, "steps": a.steps,
+                          "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": {"workload": "openlab_hybrid", "windows_per_step": n},
+                          "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", init_method="env://", device_id=dev)
+    N = a.windows
+    series_h, vmu, vsd, cmu, csd = openlab_problem(N, seed=100 + rank)
+    vae = ops.VaeScorer(synth.stage_vae_weights("openlab", seed=0), dev,
+                        engine={"auto": ops.ENGINE_AUTO, "fp32": ops.ENGINE_FP32, "tc": ops.ENGINE_TC_BF16X3}[a.engine])
+    cnn = ops.CnnOpenLab(synth.cnnol_weights(seed=0), dev)
+    pinned = torch.from_numpy(series_h).pin_memory()
+    series_d = pinned.to(dev, non_blocking=True)
+
+    def sources(sd_):
+        g = ops.WindowSource(sd_, 200, stride=20, chan=[1, 2, 3], mean=vmu, std=vsd, clip=10.0, nan_to_zero=True)
+        r = ops.WindowSource(sd_, 200, stride=20, mean=cmu, std=csd, clip=10.0, nan_to_zero=True)
+        return g, r
+
+    src_g, src_r = sources(series_d)
+    torch.manual_seed(42 + rank)
+    cal_idx = torch.linspace(0, N - 1, 2000, device=dev).to(torch.int32)
+    thr = float(ops.percentile(vae.score(src_g, torch.randn((2000, 8), device=dev), idx=cal_idx)["score"], pct).item())
+    hyb = HybridOpenLab(vae, cnn, thr, 0.5)
+    eps = torch.randn((N, 8), device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    max_flag = min(N, max(1024, int((100.0 - pct) / 100.0 * 1.5 * N)))
+    kern_ev = []
+
+    def step(timed):
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); score = vae.score(src_g, eps, n=N)["score"]; e1.record()
+            kern_ev.append((e0, e1))
+        else:
+            score = vae.score(src_g, eps, n=N)["score"]
+        flag, idx, count = ops.compact(score, thr)
+        cnn.forward(src_r, n=max_flag, idx=idx, n_dev=count, want_prob=True)
+        return count
+
+    for _ in range(a.warmup):
+        count = step(False)
+    torch.cuda.synchronize()
+    n_flag = int(count.item())
+    if n_flag > max_flag:
+        max_flag = min(N, int(1.25 * n_flag))
+        count = step(False); torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = []
+    for _ in range(a.steps):
+        flush.zero_()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(); step(True); s1.record()
+        ev.append((s0, s1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    total_ms = max_over_ranks(sum(x.elapsed_time(y) for x, y in ev), dev)
+    kern_ms = sum(x.elapsed_time(y) for x, y in kern_ev) / len(kern_ev)
+    windows_total = sum_over_ranks(float(N * a.steps), dev)
+    value = windows_total / (total_ms / 1e3)
+
+    host_score = torch.empty((N,), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        sd_ = pinned.to(dev, non_blocking=True)
+        g, r = sources(sd_)
+        res = hyb.run(g, r, torch.randn((N, 8), device=dev), n=N)
+        host_score.copy_(res["score"], non_blocking=True)
+        flags = res["flag"].cpu(); pred = res["pred"].cpu(); prob = res["prob"].cpu()
+        torch.cuda.synchronize()
+        return flags, pred, prob
+
+    e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+    if rank == 0:
+        pk = peaks()
+        eng = {ops.ENGINE_FP32: "fp32", ops.ENGINE_TC_BF16X3: "tc_bf16x3"}[vae.engine]
+        achieved = FLOP_PER_WINDOW["openlab"] * N / (kern_ms / 1e3) / 1e12
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if vae.engine == ops.ENGINE_FP32 else "bf16x3->f32", "data": "synthetic",
+            "config": {"workload": "openlab_hybrid", "windows_per_gpu": N, "T": 200, "stride": 20, "D_gate": 3, "D_raw": 4, "H": 64, "Z": 8, "L": 1,
+                       "engine": eng, "gate_threshold": f"P{pct:g} of 2000 calibration windows", "flagged_per_gpu": n_flag, "cnn_threshold": 0.5,
+                       "input": "raw 4-channel series with NaN runs, stride 20; gather+standardise fused into scorer and CNN",
+                       "l2": "flushed between timed steps (512 MiB memset)", "parallelism": f"window-range shards x{world}, no collective"},
+            "clocks": clocks,
+            "e2e": {"value": windows_total / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": int(pinned.numel() * 4),
+                    "d2h_bytes_per_step": int(N * 4 + N + 16 * n_flag + 4), "ms_per_step": 1e3 * e2e_s / a.steps,
+                    "api": "shmfast.pipeline.HybridOpenLab.run"},
+            "gpu_launches": 3 * a.steps,
+            "roofline": {"bound": "tensor", "kernel": "vae_score (fused LSTM-VAE scorer)", "achieved": achieved, "peak": pk["tf_sust"],
+                         "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"], "traffic": None, "kernel_ms": kern_ms,
+                         "peak_source": pk["source"] + " bf16 dense, sustained", "algorithmic_flop_per_window": FLOP_PER_WINDOW["openlab"],
+                         "engine": eng},
+            "cpu_baseline": None}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse_args()
-    if a.impl == "reference":
+    if a.workload == "openlab_hybrid":
+        run_openlab(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_shmfast(a)

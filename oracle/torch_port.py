@@ -129,3 +129,27 @@ def hybrid_4dof(vae: VaePort, cnn: Cnn4dofPort, series: np.ndarray, mean, std, t
         y_pred[sel] = torch.argmax(logits, dim=1).numpy().astype(np.int64) + 1
         p_struct[sel] = torch.softmax(logits, dim=1).numpy().astype(np.float32)[:, 1]
     return dict(score=score, mask=mask, idx=idx, logits=logits_all, y_pred=y_pred, p_struct=p_struct, n=N)
+
+
+@torch.no_grad()
+def hybrid_openlab(vae: VaePort, cnn: CnnOpenLabPort, series: np.ndarray, chan, vmu, vsd, cmu, csd, vae_thr: float, cnn_thr: float,
+                   eps=None, T: int = 200, stride: int = 20, batch: int = 256, clip: float = 10.0) -> dict:
+    """openLAB hot path for one stream: windowize_2d (feature_utils.py:130-152) -> gate on the selected clean
+    channels (10_test_hybrid_pipeline.py:351-367) -> CNN on the flagged raw windows with its own stats
+    (stage2_predict_cnn :265-302).  The synthetic stream serves as both X_clean and X_raw."""
+    W = np.asarray([series[i:i + T] for i in range(0, series.shape[0] - T + 1, stride)], dtype=np.float32)
+
+    def standardize(X, mu, sd):
+        Xn = (X - mu[None, None, :]) / sd[None, None, :]
+        Xn = np.clip(Xn, -clip, clip)
+        return np.nan_to_num(Xn, nan=0.0, posinf=0.0, neginf=0.0).astype(np.float32)
+
+    Xg = standardize(W[:, :, chan], vmu, vsd)
+    score = vae_scores_batched(vae, Xg, eps, batch)
+    mask = score > vae_thr
+    Xa = torch.tensor(standardize(W[mask], cmu, csd)[:, None, :, :], dtype=torch.float32)
+    probs = []
+    for i in range(0, Xa.shape[0], batch):
+        probs.append(torch.softmax(cnn(Xa[i:i + batch]), dim=1)[:, 1].numpy())
+    prob = np.concatenate(probs, axis=0).astype(np.float64) if probs else np.zeros((0,), np.float64)
+    return dict(score=score, mask=mask, prob=prob, pred=(prob >= cnn_thr).astype(np.int64), n=W.shape[0])
