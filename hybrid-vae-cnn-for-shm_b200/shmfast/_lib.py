@@ -68,6 +68,14 @@ SIGNATURES = {
     "shm_vae_debug_counters": (C.c_int, [_vp, _vp, C.c_int]),
     "shm_vae_score": (C.c_int, [_vp, C.POINTER(WindowSrc), _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "shm_vae_decode": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, _vp]),
+    "shm_vae_param_count": (C.c_int64, [C.POINTER(VaeCfg)]),
+    "shm_vae_trainer_create": (C.c_int, [C.POINTER(_vp), C.POINTER(VaeCfg), C.c_int32, C.c_int32, C.c_int]),
+    "shm_vae_trainer_destroy": (C.c_int, [_vp]),
+    "shm_vae_train_forward": (C.c_int, [_vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp]),
+    "shm_vae_train_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "shm_vae_elbo_grad": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_float, _vp, _vp, _vp, _vp, _vp]),
+    "shm_adam_clip_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
+                                     C.c_float, C.c_float, C.c_float, _vp, _vp]),
     "shm_compact_workspace_bytes": (C.c_int64, [C.c_int64]),
     "shm_compact": (C.c_int, [_vp, C.c_float, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "shm_cnn4dof_create": (C.c_int, [C.POINTER(_vp), C.POINTER(Cnn4dofWeights), C.c_int]),

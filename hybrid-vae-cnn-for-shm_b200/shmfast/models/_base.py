@@ -47,6 +47,7 @@ class TemporalVAEBase(nn.Module):
         self.output_layer = nn.Linear(hidden_dim, input_dim)
         self._scorer = None
         self._sig = None
+        self._trainer = None
 
     # -- handle management -------------------------------------------------------------------
     def scorer(self) -> ops.VaeScorer:
@@ -72,11 +73,23 @@ class TemporalVAEBase(nn.Module):
             raise ShmfastError("input is a CPU tensor: libshmfast has no CPU fallback")
         if x.dim() != 3 or x.shape[2] != self.input_dim:
             raise ShmfastError(f"expected [B, T, {self.input_dim}], got {tuple(x.shape)}")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())) and self.training:
-            raise NotImplementedError(
-                "training through the shim is not wired yet: use shmfast.train.VaeTrainer (DDP step) "
-                "or call under torch.no_grad()/eval()")
         return x.detach().to(torch.float32).contiguous()
+
+    def _train_forward(self, x: torch.Tensor):
+        """train() mode (03_train_vae.py:262): same kernels as shmfast.train.VaeTrainer, bridged into autograd so the
+        reference's loss.backward() / clip_grad_norm_ / opt.step() lines run unchanged.  Inter-layer dropout masks and
+        eps are drawn with torch's generator on the device and handed to the kernels."""
+        from .. import train as _train
+        B, T, _ = x.shape
+        h = self._trainer
+        if h is None or h.T != T or h.max_batch < B or h.device != x.device:
+            if h is not None:
+                h.close()
+            h = self._trainer = _train.VaeTrainHandle(_train.vae_cfg_of(self), T, B, x.device)
+        p = float(self.encoder_lstm.dropout)
+        enc, dec = _train.draw_dropout_masks(self.num_layers, B, T, self.hidden_dim, p, x.device)
+        eps = torch.randn((B, self.latent_dim), dtype=torch.float32, device=x.device)
+        return _train.VaeTrainFunction.apply(h, x, eps, enc, dec, p, *self.parameters())
 
     # -- reference surface -------------------------------------------------------------------
     def encode(self, x: torch.Tensor):
@@ -97,6 +110,8 @@ class TemporalVAEBase(nn.Module):
 
     def forward(self, x: torch.Tensor):
         x = self._check_input(x)
+        if self.training:
+            return self._train_forward(x)
         # the reference draws eps = torch.randn_like(std) inside forward() even in eval mode
         # (temporal_vae.py:60-63); the same call on the same generator keeps the RNG stream identical.
         eps = torch.randn((x.shape[0], self.latent_dim), dtype=torch.float32, device=x.device)

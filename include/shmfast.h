@@ -156,6 +156,54 @@ int shm_vae_score(shm_vae* h, const shm_window_src* src_host, const int32_t* idx
 int shm_vae_decode(shm_vae* h, const float* z, int64_t n, int32_t T, float* recon, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * LSTM-VAE training step (BASELINE config 5): the inner loop of 4DOF/Scripts/03_train_vae.py:260-271
+ *     xhat, mu, logvar = vae(xb); recon = mse_loss(xhat, xb); kl = -0.5*mean(1+logvar-mu^2-exp(logvar));
+ *     loss = recon + kl_w*kl; loss.backward(); clip_grad_norm_(params, 2.0); opt.step()   # Adam, wd=1e-5
+ * as four entry points, so that either the reference's own loop drives them through an autograd
+ * Function (forward / backward) or a fused trainer calls all four with one gradient all-reduce between
+ * backward and the optimiser step (data parallel).
+ *
+ * `params` / `grads` / `exp_avg` / `exp_avg_sq` are flat fp32 device buffers of shm_vae_param_count(cfg)
+ * elements in list(model.parameters()) order (temporal_vae.py:29-49): per encoder layer weight_ih, weight_hh,
+ * bias_ih, bias_hh; layer_norm.{weight,bias} (if has_ln); fc_mu.{weight,bias}; fc_logvar.{weight,bias};
+ * fc_latent_to_hidden.{weight,bias}; per decoder layer the same four; output_layer.{weight,bias}.
+ * The caller owns them; the trainer handle owns only the activation workspace for (T, max_batch).
+ * Supported shapes: as shm_vae_cfg (H in {32,64,128}, L <= 2, Z <= 16); cfg->engine is ignored (fp32).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct shm_vae_trainer shm_vae_trainer;
+int64_t shm_vae_param_count(const shm_vae_cfg* cfg_host);
+int shm_vae_trainer_create(shm_vae_trainer** out, const shm_vae_cfg* cfg_host, int32_t T, int32_t max_batch, int device);
+int shm_vae_trainer_destroy(shm_vae_trainer* h);
+
+/* TemporalVAE.forward in train() mode (temporal_vae.py:72-77) for x [B,T,D]; activations are kept in the handle
+ * for the backward pass.
+ *   eps       : [B,Z] the reparameterisation noise (torch.randn_like, temporal_vae.py:62)
+ *   drop_enc / drop_dec : optional uint8 keep-masks [L-1][B,T,H] for the inter-layer dropout of nn.LSTM
+ *               (temporal_vae.py:33,47; 1 = keep, kept values are scaled by 1/(1-drop_p)); both NULL = no dropout
+ *   xhat [B,T,D], mu [B,Z], logvar [B,Z] : outputs (each optional) */
+int shm_vae_train_forward(shm_vae_trainer* h, const float* params, const float* x, int32_t B, const float* eps,
+                          const uint8_t* drop_enc, const uint8_t* drop_dec, float drop_p, float* xhat, float* mu,
+                          float* logvar, void* stream);
+
+/* Back-propagation through time of the last shm_vae_train_forward: upstream gradients d_xhat [B,T,D] and
+ * (optional) d_mu, d_logvar [B,Z] -> grads (flat, overwritten).  One backward per forward. */
+int shm_vae_train_backward(shm_vae_trainer* h, const float* params, const float* d_xhat, const float* d_mu,
+                           const float* d_logvar, float* grads, void* stream);
+
+/* ELBO of 03_train_vae.py:264-266 and its gradients w.r.t. xhat / mu / logvar (each optional):
+ * loss3 = device float[3] {recon + kl_w*kl, recon, kl}; n_x = B*T*D, n_z = B*Z. */
+int shm_vae_elbo_grad(const float* x, const float* xhat, const float* mu, const float* logvar, int64_t n_x, int64_t n_z,
+                      float kl_w, float* d_xhat, float* d_mu, float* d_logvar, float* loss3, void* stream);
+
+/* torch.nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam.step (weight_decay added to the
+ * gradient, bias-corrected; 03_train_vae.py:222,269-270) over flat buffers.  `grads` is read as grads*grad_scale
+ * (1/world_size after a SUM all-reduce).  step >= 1 is the Adam step count AFTER this update.  max_norm <= 0
+ * disables clipping.  norm2 = device float[2]: {sum of squares of grads, total norm returned by clip_grad_norm_}. */
+int shm_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t step,
+                       float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                       float* norm2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Threshold + routing: mask = score > thr (strict, fp32), idx = np.where(mask)[0] ascending
  * (06_test_full_pipeline.py:350-351, 10_test_hybrid_pipeline.py:367).
  *   flag  : optional uint8[N];  idx : int32[N] (first *count entries valid);  count : device int32

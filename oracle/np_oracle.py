@@ -415,3 +415,22 @@ def hybrid_openlab(vae_sd, cnn_sd, X_clean, X_raw, channels_idx, vae_mu, vae_sd_
         logits[j:j + batch] = cnnol_forward(cnn_sd, Xa[j:j + batch], dtype)
     pred, p = cnnol_decision(logits, cnn_thr)
     return dict(score=score, mask=mask, idx=idx, logits=logits, pred=pred, prob=p)
+
+
+def adam_clip_step(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, wd=1e-5, max_norm=2.0, grad_scale=1.0):
+    """torch.nn.utils.clip_grad_norm_(max_norm) + torch.optim.Adam.step (weight_decay as L2-in-grad) over flat fp32
+    arrays, 4DOF/Scripts/03_train_vae.py:222,269-270.  Returns (p, m, v, total_norm); `g` is read as g*grad_scale."""
+    f = np.float32
+    g = (g.astype(f) * f(grad_scale)).astype(f)
+    total = f(np.sqrt(np.sum(g.astype(np.float64) ** 2)))
+    if max_norm > 0:
+        coef = min(1.0, float(max_norm) / (float(total) + 1e-6))
+        g = (g * f(coef)).astype(f)
+    g = (g + f(wd) * p).astype(f)
+    m = (f(b1) * m + f(1 - b1) * g).astype(f)
+    v = (f(b2) * v + f(1 - b2) * g * g).astype(f)
+    bc1 = 1.0 - b1 ** step
+    bc2s = np.sqrt(1.0 - b2 ** step)
+    denom = (np.sqrt(v) / f(bc2s) + f(eps)).astype(f)
+    p = (p - f(lr / bc1) * (m / denom)).astype(f)
+    return p, m, v, float(total)

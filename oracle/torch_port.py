@@ -153,3 +153,98 @@ def hybrid_openlab(vae: VaePort, cnn: CnnOpenLabPort, series: np.ndarray, chan, 
         probs.append(torch.softmax(cnn(Xa[i:i + batch]), dim=1)[:, 1].numpy())
     prob = np.concatenate(probs, axis=0).astype(np.float64) if probs else np.zeros((0,), np.float64)
     return dict(score=score, mask=mask, prob=prob, pred=(prob >= cnn_thr).astype(np.int64), n=W.shape[0])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# training step (BASELINE config 5): 4DOF/Scripts/03_train_vae.py:260-271
+# ---------------------------------------------------------------------------------------------------------
+PARAM_ORDER_DOC = "list(model.parameters()) order of TemporalVAE (temporal_vae.py:29-49)"
+
+
+def vae_param_names(sd: dict) -> list:
+    """State-dict keys in list(model.parameters()) order (the flat layout of include/shmfast.h)."""
+    L = sum(1 for k in sd if k.startswith("encoder_lstm.weight_ih_l"))
+    names = []
+    for l in range(L):
+        names += [f"encoder_lstm.{k}_l{l}" for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+    if "layer_norm.weight" in sd:
+        names += ["layer_norm.weight", "layer_norm.bias"]
+    names += ["fc_mu.weight", "fc_mu.bias", "fc_logvar.weight", "fc_logvar.bias", "fc_latent_to_hidden.weight",
+              "fc_latent_to_hidden.bias"]
+    for l in range(L):
+        names += [f"decoder_lstm.{k}_l{l}" for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+    names += ["output_layer.weight", "output_layer.bias"]
+    return names
+
+
+class VaeTrainPort(nn.Module):
+    """TemporalVAE.forward in train() mode (temporal_vae.py:51-77) with the random draws made explicit: eps is
+    supplied, and nn.LSTM's inter-layer dropout (temporal_vae.py:33,47) is written out as a stack of single-layer
+    nn.LSTMs with supplied keep-masks (with no mask the stack is arithmetically the reference's multi-layer nn.LSTM;
+    checked against the reference module's gradients in tests/test_oracle_golden.py)."""
+
+    def __init__(self, sd: dict):
+        super().__init__()
+        w = sd["encoder_lstm.weight_ih_l0"]
+        H, D = w.shape[0] // 4, w.shape[1]
+        L = sum(1 for k in sd if k.startswith("encoder_lstm.weight_ih_l"))
+        Z = sd["fc_mu.weight"].shape[0]
+        self.L = L
+        self.enc = nn.ModuleList([nn.LSTM(D if l == 0 else H, H, 1, batch_first=True) for l in range(L)])
+        self.dec = nn.ModuleList([nn.LSTM(H, H, 1, batch_first=True) for l in range(L)])
+        self.ln = nn.LayerNorm(H) if "layer_norm.weight" in sd else None
+        self.mu, self.lv = nn.Linear(H, Z), nn.Linear(H, Z)
+        self.l2h, self.out = nn.Linear(Z, H), nn.Linear(H, D)
+        self.names = vae_param_names(sd)
+        with torch.no_grad():
+            for name in self.names:
+                self.param(name).copy_(_t(np.asarray(sd[name], dtype=np.float32)))
+
+    def param(self, name: str) -> nn.Parameter:
+        mod, rest = name.split(".", 1)
+        if mod in ("encoder_lstm", "decoder_lstm"):
+            kind, l = rest.rsplit("_l", 1)
+            return getattr((self.enc if mod == "encoder_lstm" else self.dec)[int(l)], kind + "_l0")
+        m = {"layer_norm": self.ln, "fc_mu": self.mu, "fc_logvar": self.lv, "fc_latent_to_hidden": self.l2h,
+             "output_layer": self.out}[mod]
+        return getattr(m, rest)
+
+    def ordered_parameters(self) -> list:
+        return [self.param(n) for n in self.names]
+
+    def _stack(self, layers, x, masks, p):
+        for l, lstm in enumerate(layers):
+            x, (h_n, _) = lstm(x)
+            if l < self.L - 1 and masks is not None:
+                x = x * masks[l].to(x.dtype) / (1.0 - p)
+        return x, h_n[-1]
+
+    def forward(self, x, eps, drop_enc=None, drop_dec=None, p: float = 0.0):
+        _, h = self._stack(self.enc, x, drop_enc, p)
+        if self.ln is not None:
+            h = self.ln(h)
+        mu, lv = self.mu(h), self.lv(h)
+        z = mu + eps * torch.exp(0.5 * lv)
+        u = torch.tanh(self.l2h(z)).unsqueeze(1).repeat(1, x.size(1), 1)
+        y, _ = self._stack(self.dec, u, drop_dec, p)
+        return self.out(y), mu, lv
+
+
+def train_step_port(port: VaeTrainPort, opt, x, eps, kl_w: float, drop_enc=None, drop_dec=None, p: float = 0.0,
+                    max_norm: float = 2.0, world: int = 1):
+    """03_train_vae.py:262-270 on the port.  Returns (loss3, flat gradient before clipping, total_norm)."""
+    xhat, mu, logvar = port(x, eps, drop_enc, drop_dec, p)
+    recon = F.mse_loss(xhat, x, reduction="mean")
+    kl = -0.5 * torch.mean(1.0 + logvar - mu.pow(2) - logvar.exp())
+    loss = recon + kl_w * kl
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    params = port.ordered_parameters()
+    flat_g = torch.cat([q.grad.reshape(-1) for q in params]).clone()
+    total = torch.nn.utils.clip_grad_norm_(params, max_norm=max_norm) if max_norm > 0 else torch.linalg.vector_norm(flat_g)
+    opt.step()
+    return np.array([loss.item(), recon.item(), kl.item()]), flat_g.numpy(), float(total)
+
+
+def flat_params(port: VaeTrainPort) -> np.ndarray:
+    return torch.cat([q.detach().reshape(-1) for q in port.ordered_parameters()]).numpy().copy()

@@ -141,3 +141,55 @@ def test_graft_entry_build_and_bench_cli():
     ge.build()
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "--impl" in r.stdout and "--gpus" in r.stdout
+
+
+DDP_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["SHM_PKG"]); sys.path.insert(0, os.environ["SHM_ROOT"])
+from shmfast import synth, train
+from oracle import np_oracle as O, torch_port as TP
+dist.init_process_group("gloo", init_method="env://")
+rank, world = dist.get_rank(), dist.get_world_size()
+D, Z, H, L, B, T = 12, 16, 32, 2, 8, 40
+X, eps = synth.windows(B, T, D, seed=1), synth.eps(B, Z, seed=2)
+
+def local_grad(sd, lo, hi):                       # the oracle stands in for the CUDA forward/backward of one rank
+    port = TP.VaeTrainPort(sd).train()
+    opt = torch.optim.SGD(port.ordered_parameters(), lr=0.0)
+    _, g, _ = TP.train_step_port(port, opt, torch.from_numpy(X[lo:hi]), torch.from_numpy(eps[lo:hi]), 0.5, max_norm=0.0)
+    return TP.flat_params(port), g
+
+# replicas start different; broadcast_parameters makes rank 0's weights win (DDP constructor semantics)
+sd = synth.vae_weights(D, H, Z, L, True, seed=10 + rank)
+names = TP.vae_param_names(sd)
+flat = torch.from_numpy(np.concatenate([sd[n].reshape(-1) for n in names]))
+train.broadcast_parameters(flat)
+sd0 = synth.vae_weights(D, H, Z, L, True, seed=10)
+assert np.array_equal(flat.numpy(), np.concatenate([sd0[n].reshape(-1) for n in names]))
+lo, hi = rank * B // world, (rank + 1) * B // world
+p, g = local_grad(sd0, lo, hi)
+gt = torch.from_numpy(g.copy())
+scale = train.reduce_gradients(gt)                # the one collective: SUM, scale = 1/world applied by the optimiser
+assert scale == 1.0 / world
+p_new, _, _, norm = O.adam_clip_step(p, gt.numpy(), np.zeros_like(p), np.zeros_like(p), 1, max_norm=0.05, grad_scale=scale)
+p_full, g_full = local_grad(sd0, 0, B)            # what one rank with the whole batch computes
+p_ref, _, _, norm_ref = O.adam_clip_step(p_full, g_full, np.zeros_like(p), np.zeros_like(p), 1, max_norm=0.05)
+assert abs(norm - norm_ref) <= 1e-5 * norm_ref, (norm, norm_ref)
+assert np.max(np.abs(gt.numpy() * scale - g_full)) <= 1e-5 * np.max(np.abs(g_full))
+assert np.mean(np.abs(p_new - p_ref) <= 1e-6) > 0.98
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_data_parallel_step_two_ranks_gloo(tmp_path):
+    """Host-side protocol of the data-parallel training step (shmfast.train.broadcast_parameters /
+    reduce_gradients + the 1/world scale consumed by the optimiser) with world_size 2 on gloo."""
+    script = tmp_path / "ddp_worker.py"
+    script.write_text(DDP_WORKER)
+    env = dict(os.environ, SHM_PKG=str(ROOT / "hybrid-vae-cnn-for-shm_b200"), SHM_ROOT=str(ROOT), MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2

@@ -160,3 +160,39 @@ def test_torch_port_matches_goldens(golden_dir):
         vae, cnn = TP.VaePort(vae_sd), TP.Cnn4dofPort(cnn_sd)
         score = TP.vae_scores_batched(vae, g["Z"], synth.eps(g["Z"].shape[0], 16, seed=41), 512)
         assert _rel(score, g["score"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["small", "full"])
+def test_train_step_port_matches_reference(golden_dir, name):
+    """oracle/torch_port.VaeTrainPort + np_oracle.adam_clip_step against one optimisation step executed on the
+    reference's own TemporalVAE (tests/golden/make_golden.py::train_fixtures)."""
+    import torch
+    from oracle import torch_port as TP
+    g = np.load(golden_dir / f"train_step_{name}.npz")
+    D, Z, H, L, B, T = (int(g[k]) for k in "DZHLBT")
+    seed, kl_w = int(g["seed"]), float(g["kl_w"])
+    sd = synth.vae_weights(D, H, Z, L, True, seed=seed)
+    port = TP.VaeTrainPort(sd).train()
+    p0 = TP.flat_params(port)
+    opt = torch.optim.Adam(port.ordered_parameters(), lr=1e-3, weight_decay=1e-5)
+    x, eps = torch.from_numpy(synth.windows(B, T, D, seed=seed)), torch.from_numpy(synth.eps(B, Z, seed=seed))
+    loss3, fg, total = TP.train_step_port(port, opt, x, eps, kl_w)
+    assert np.allclose(loss3, g["loss3"], rtol=1e-6)
+    assert abs(total - float(g["total_norm"])) <= 1e-6 * float(g["total_norm"])
+    p1 = TP.flat_params(port)
+    p_np, _, _, total_np = O.adam_clip_step(p0, fg, np.zeros_like(p0), np.zeros_like(p0), 1)
+    assert abs(total_np - total) <= 1e-6 * total
+    assert np.max(np.abs(p_np - p1)) <= 2e-7            # numpy restatement of clip + Adam == torch.optim.Adam
+    o = 0
+    for n in port.names:
+        k = port.param(n).numel()
+        got_g, got_p = fg[o:o + k], p1[o:o + k]
+        if name == "full":
+            got_g, got_p = got_g[g["i:" + n]], got_p[g["i:" + n]]
+        ref_g, ref_p = g["g:" + n].reshape(-1), g["p:" + n].reshape(-1)
+        assert np.max(np.abs(got_g - ref_g)) <= 2e-6 * (np.max(np.abs(ref_g)) + 1e-12), n
+        # Adam's first step moves every weight by ~lr*sign(g): entries with |g| near fp32 noise may flip
+        assert np.max(np.abs(got_p - ref_p)) <= 2.1e-3, n
+        assert np.mean(np.abs(got_p - ref_p) <= 1e-6) > 0.97, n
+        o += k
+    assert o == fg.size
