@@ -43,6 +43,9 @@ METRIC = "windows/sec (VAE score + CNN attribution)"
 # algorithmic work per window, SURVEY.md section 8(d) / BASELINE.md section 3
 FLOP_PER_WINDOW = {"4dof": 80_322_560, "openlab": 13_527_040, "1dof": 4_248_512}
 CNN_FLOP_PER_FLAGGED = {"4dof": 4_070_912, "openlab": 133_851_648}
+# ncu --set full capture of vae_score_tc_kernel<128> (profiles/r01_vae_tc_raw.csv): 15.577 GB read + 15.581 GB written
+# for a 151,552-window launch
+NCU_DRAM_BYTES_PER_WINDOW_4DOF = (15.577271e9 + 15.580796e9) / 151552
 
 
 def parse_args():
@@ -303,9 +306,30 @@ def run_shmfast(a):
                "api": "shmfast.pipeline.Hybrid4dof.run + scatter (host pinned series in, scores/labels/p_struct out)"}
 
     cpu_baseline = None
+    torch_cuda = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         r = cpu_port_run(min(a.cpu_sample, N), 1, 1, thr, a.workload)
         cpu_baseline = {"value": r["value"], "unit": "windows/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        # the incumbent on the same GPU: the reference's wiring on stock PyTorch CUDA kernels
+        # (cuDNN LSTM / conv), batch 512 with the reference's per-batch host<->device copies.  Baseline leg only.
+        try:
+            from oracle import torch_port as TP
+            ns = min(65536, N)
+            vae_c = TP.VaePort(synth.stage_vae_weights("4dof", seed=0)).to(dev)
+            cnn_c = TP.Cnn4dofPort(synth.cnn4dof_weights(seed=0)).to(dev)
+            ser = series_h[: ns + T - 1]
+            TP.hybrid_4dof_device(vae_c, cnn_c, ser[: 4096 + T - 1], mean, std, thr, dev)      # warm-up (cuDNN plans)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rc_ = TP.hybrid_4dof_device(vae_c, cnn_c, ser, mean, std, thr, dev)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            torch_cuda = {"value": ns / dt, "unit": "windows/s", "kind": "port on torch CUDA kernels (cuDNN LSTM/conv), fp32",
+                          "sample": f"{ns} windows, batch 512, host windows + per-batch H2D/D2H as the reference does",
+                          "flagged": int(rc_["idx"].size)}
+            del vae_c, cnn_c
+        except Exception as e:                                   # a baseline must never break the bench line
+            torch_cuda = {"unavailable": repr(e)[:200]}
 
     if rank == 0:
         eng_name = {ops.ENGINE_FP32: "fp32", ops.ENGINE_TC_BF16X3: "tc_bf16x3"}[vae.engine]
@@ -322,10 +346,14 @@ def run_shmfast(a):
                        "l2": "flushed between timed steps (512 MiB memset)", "parallelism": f"window-range shards x{world}, no collective"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
             "roofline": {"bound": "tensor", "kernel": "vae_score (fused LSTM-VAE scorer, first pass)", "achieved": achieved,
-                         "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"], "traffic": None,
+                         "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
+                         "traffic": NCU_DRAM_BYTES_PER_WINDOW_4DOF * N if vae.engine == ops.ENGINE_TC_BF16X3 else None,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_vae_tc_raw.csv (151,552-window "
+                                         "launch: 31.16 GB) scaled per window; it is the layer-0 h_t stream (T x 64 KB per tile, "
+                                         "written once + read once), not input re-reads: the input is 48 B/window",
                          "peak_source": pk["source"] + " bf16 dense, sustained", "kernel_ms": kern_ms,
                          "algorithmic_flop_per_window": FLOP_PER_WINDOW["4dof"], "engine": eng_name},
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "torch_cuda_baseline": torch_cuda,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

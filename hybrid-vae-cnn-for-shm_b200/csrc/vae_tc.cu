@@ -127,18 +127,20 @@ struct EpiCtx {
 
 // One chunk (32 hidden units x 4 gates) of one step for this thread's (row, 16-unit) slice, in two batches of
 // 8 units to bound register pressure: TMEM -> registers, LSTM cell, h_t -> TMEM (fp16 hi|lo) and the pass's sink.
-template <int H, int C, int SINK>
-__device__ __forceinline__ void epi_chunk(const EpiCtx& x, uint32_t& nacc, float (&cst)[16]) {
+// `c` is a RUN-TIME chunk index: the chunk loop is a real loop (the cell state rotates through the register arrays),
+// so the hot loop of the epilogue is ~11 KB of code instead of ~41 KB -- the fully unrolled form overflowed the 32 KB
+// L1.5 instruction cache (ncu: 25 % of the epilogue's issue slots were stall_no_inst).
+template <int H, int SINK>
+__device__ __forceinline__ void epi_chunk(const EpiCtx& x, int c, uint32_t acc_parity, float (&cst)[16]) {
     using S = TcSmem<H>;
-    constexpr int b = C & 1;
+    const int b = c & 1;
     {
         const long long tw0 = clock64();
-        mbar_wait(&x.bars->acc_full[b], nacc & 1);
-        x.prof[C < 3 ? C : 2] += clock64() - tw0;
+        mbar_wait(&x.bars->acc_full[b], acc_parity);
+        x.prof[0] += clock64() - tw0;
     }
-    ++nacc;
     tc_fence_after_sync();
-    const int ub = C * 32 + x.wg * 16;                              // first hidden unit of this thread's slice
+    const int ub = c * 32 + x.wg * 16;                              // first hidden unit of this thread's slice
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         uint32_t g0[8], g1[8], g2[8], g3[8];
@@ -147,11 +149,7 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& x, uint32_t& nacc, float
         tmem_ld8(abase + 32, g1);
         tmem_ld8(abase + 64, g2);
         tmem_ld8(abase + 96, g3);
-        {
-            const long long tl0 = clock64();
-            tmem_ld_wait();
-            if (C == 3) x.prof[3] += clock64() - tl0; else x.prof[3] += clock64() - tl0;
-        }
+        tmem_ld_wait();
         if (half == 1) {                                             // accumulator slice fully in registers: release it
             tc_fence_before_sync();
             __syncwarp();
@@ -219,10 +217,21 @@ __device__ __forceinline__ void epi_pass(const PassCtx& pc, const VaeDev& P, con
         const uint32_t hbuf = pc.t_h + (uint32_t)((t & 1) * H);
         EpiCtx ctx{pc.bars, pc.t_acc, hbuf, lane_base, pc.bias_s, pc.scratch + (size_t)t * S::IMG,
                    reinterpret_cast<float*>(pc.inbuf + pc.hT_buf * S::IMG), wg, row, lane, t == T - 1, prof};
-        epi_chunk<H, 0, SINK>(ctx, nacc0, cst[0]);
-        if constexpr (NCH > 1) epi_chunk<H, 1, SINK>(ctx, nacc1, cst[1]);
-        if constexpr (NCH > 2) epi_chunk<H, 2, SINK>(ctx, nacc0, cst[2]);
-        if constexpr (NCH > 3) epi_chunk<H, 3, SINK>(ctx, nacc1, cst[3]);
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+            const uint32_t par = ((c & 1) ? nacc1 : nacc0) & 1;
+            if (c & 1) ++nacc1; else ++nacc0;
+            epi_chunk<H, SINK>(ctx, c, par, cst[0]);
+            if constexpr (NCH > 1) {                           // rotate the cell state: chunk c+1's state moves to cst[0]
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const float t0 = cst[0][u];
+#pragma unroll
+                    for (int k = 0; k + 1 < NCH; ++k) cst[k][u] = cst[k + 1][u];
+                    cst[NCH - 1][u] = t0;
+                }
+            }
+        }
         tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
@@ -688,7 +697,8 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
                 if (sink == SINK_STREAM) epi_pass<H, SINK_STREAM>(pc, P, src, io, TC.pass[p].bias, acc_base, prof);
                 else if (sink == SINK_LAST_ENC) epi_pass<H, SINK_LAST_ENC>(pc, P, src, io, TC.pass[p].bias, acc_base, prof);
                 else epi_pass<H, SINK_LAST_DEC>(pc, P, src, io, TC.pass[p].bias, acc_base, prof);
-                prof[4 + (p & 3)] += clock64() - pass_t0;
+                { const long long _d = clock64() - pass_t0; const int _q = p & 3;
+                  if (_q == 0) prof[4] += _d; else if (_q == 1) prof[5] += _d; else if (_q == 2) prof[6] += _d; else prof[7] += _d; }
                 cta_sync();                        // (B) end of pass
                 pass_advance(in_kind, sink);
             }
@@ -714,7 +724,8 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
                     } else if (in_kind == IN_X) mma_pass<H, IN_X, false>(pc, ring_base, in_base, acc_base, h_base, xhat_base, prof);
                     else if (in_kind == IN_STREAM) mma_pass<H, IN_STREAM, false>(pc, ring_base, in_base, acc_base, h_base, xhat_base, prof);
                     else mma_pass<H, IN_CONST, false>(pc, ring_base, in_base, acc_base, h_base, xhat_base, prof);
-                    prof[4 + (p & 3)] += clock64() - pass_t0;
+                    { const long long _d = clock64() - pass_t0; const int _q = p & 3;
+                  if (_q == 0) prof[4] += _d; else if (_q == 1) prof[5] += _d; else if (_q == 2) prof[6] += _d; else prof[7] += _d; }
                 } else if (warp >= TC_WARP_AUX0 && warp < TC_WARP_AUX0 + 4) {
                     if (in_kind == IN_X) aux_stage_pass(pc, P, src, io, in_base, prof);
                     if (sink == SINK_LAST_DEC) aux_out_pass<H>(pc, P, src, io, xhat_base, prof);

@@ -132,6 +132,32 @@ def hybrid_4dof(vae: VaePort, cnn: Cnn4dofPort, series: np.ndarray, mean, std, t
 
 
 @torch.no_grad()
+def hybrid_4dof_device(vae: VaePort, cnn: Cnn4dofPort, series: np.ndarray, mean, std, thr: float, device, T: int = 100,
+                       stride: int = 1, batch: int = 512) -> dict:
+    """hybrid_4dof with the models on `device` (the incumbent: stock PyTorch kernels -- cuDNN LSTM, cuDNN conv -- on the
+    GPU), keeping the reference's data movement: windows are built on the host, every batch goes host -> device and its
+    scores / logits come back device -> host (06_test_full_pipeline.py:338-344,358-372).  Baseline timing only."""
+    W = np.stack([series[i:i + T] for i in range(0, series.shape[0] - T + 1, stride)], axis=0).astype(np.float32)
+    Z = np.nan_to_num((W - mean[None, None, :]) / std[None, None, :], nan=0.0, posinf=0.0, neginf=0.0).astype(np.float32)
+    N = Z.shape[0]
+    score = np.zeros((N,), np.float32)
+    Zn = vae.mu.out_features
+    for i in range(0, N, batch):
+        xb = torch.tensor(Z[i:i + batch], dtype=torch.float32).to(device)
+        xhat, _, _ = vae(xb, torch.randn((xb.shape[0], Zn), device=device))
+        score[i:i + batch] = ((xb - xhat) ** 2).mean(dim=(1, 2)).detach().cpu().numpy().astype(np.float32)
+    idx = np.where(score > thr)[0]
+    y_pred = np.zeros((N,), np.int64)
+    for j in range(0, idx.size, batch):
+        sel = idx[j:j + batch]
+        zb = torch.tensor(Z[sel], dtype=torch.float32).to(device)
+        xhat, _, _ = vae(zb, torch.randn((zb.shape[0], Zn), device=device))
+        logits = cnn(torch.stack([zb, (zb - xhat) ** 2], dim=1))
+        y_pred[sel] = torch.argmax(logits, dim=1).cpu().numpy().astype(np.int64) + 1
+    return dict(score=score, idx=idx, y_pred=y_pred, n=N)
+
+
+@torch.no_grad()
 def hybrid_openlab(vae: VaePort, cnn: CnnOpenLabPort, series: np.ndarray, chan, vmu, vsd, cmu, csd, vae_thr: float, cnn_thr: float,
                    eps=None, T: int = 200, stride: int = 20, batch: int = 256, clip: float = 10.0) -> dict:
     """openLAB hot path for one stream: windowize_2d (feature_utils.py:130-152) -> gate on the selected clean
