@@ -67,7 +67,7 @@ struct GemmArgs {
 };
 
 template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmArgs g) {
     constexpr int BK = 16;
     constexpr int NI = TM / 4, NJ = TN / 4;
     constexpr int TX = BN / TN;                  // thread columns
@@ -84,35 +84,48 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
+    // global -> registers -> shared, one tile ahead: the loads of tile k+1 are in flight while tile k is multiplied
+    constexpr int NA = BM * BK / 256, NB = BN * BK / 256;
+    float ra[NA], rb[NB];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int e = 0; e < NA; ++e) {
+            const int i = tid + e * 256;
+            int m, k;
+            if (g.a_ks == 1) { k = i % BK; m = i / BK; } else { m = i % BM; k = i / BM; }     // fastest index along the contiguous dim
+            const int gm = m0 + m, gk = k0 + k;
+            ra[e] = (gm < g.M && gk < kend) ? __ldg(g.A + (long long)gm * g.a_ms + (long long)gk * g.a_ks) : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < NB; ++e) {
+            const int i = tid + e * 256;
+            int n, k;
+            if (g.b_ks == 1) { k = i % BK; n = i / BK; } else { n = i % BN; k = i / BN; }
+            const int gn = n0 + n, gk = k0 + k;
+            rb[e] = (gn < g.N && gk < kend) ? __ldg(g.B + (long long)gk * g.b_ks + (long long)gn * g.b_ns) : 0.f;
+        }
+    };
+    auto commit = [&]() {
+#pragma unroll
+        for (int e = 0; e < NA; ++e) {
+            const int i = tid + e * 256;
+            int m, k;
+            if (g.a_ks == 1) { k = i % BK; m = i / BK; } else { m = i % BM; k = i / BM; }
+            As[k][m] = ra[e];
+        }
+#pragma unroll
+        for (int e = 0; e < NB; ++e) {
+            const int i = tid + e * 256;
+            int n, k;
+            if (g.b_ks == 1) { k = i % BK; n = i / BK; } else { n = i % BN; k = i / BN; }
+            Bs[k][n] = rb[e];
+        }
+    };
+    if (kbeg < kend) fetch(kbeg);
     for (int k0 = kbeg; k0 < kend; k0 += BK) {
-        // stage A tile: fastest thread index along the contiguous dimension
-        if (g.a_ks == 1) {
-            for (int i = tid; i < BM * BK; i += 256) {
-                const int k = i % BK, m = i / BK;
-                const int gm = m0 + m, gk = k0 + k;
-                As[k][m] = (gm < g.M && gk < kend) ? __ldg(g.A + (long long)gm * g.a_ms + gk) : 0.f;
-            }
-        } else {
-            for (int i = tid; i < BM * BK; i += 256) {
-                const int m = i % BM, k = i / BM;
-                const int gm = m0 + m, gk = k0 + k;
-                As[k][m] = (gm < g.M && gk < kend) ? __ldg(g.A + (long long)gm * g.a_ms + (long long)gk * g.a_ks) : 0.f;
-            }
-        }
-        if (g.b_ks == 1) {
-            for (int i = tid; i < BN * BK; i += 256) {
-                const int k = i % BK, n = i / BK;
-                const int gn = n0 + n, gk = k0 + k;
-                Bs[k][n] = (gn < g.N && gk < kend) ? __ldg(g.B + (long long)gn * g.b_ns + gk) : 0.f;
-            }
-        } else {
-            for (int i = tid; i < BN * BK; i += 256) {
-                const int n = i % BN, k = i / BN;
-                const int gn = n0 + n, gk = k0 + k;
-                Bs[k][n] = (gn < g.N && gk < kend) ? __ldg(g.B + (long long)gk * g.b_ks + (long long)gn * g.b_ns) : 0.f;
-            }
-        }
+        commit();
         __syncthreads();
+        if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             float a[TM], b[TN];
@@ -158,7 +171,8 @@ static int gemm(cudaStream_t st, const float* A, long long a_ms, long long a_ks,
     if (M <= 0 || N <= 0 || K <= 0) return SHM_OK;
     GemmArgs g{A, a_ms, a_ks, B, b_ks, b_ns, C, ldc, M, N, K, bias1, bias2, K, splitk ? 1 : 0};
     const bool narrow = N <= 16;
-    const int BM = narrow ? 256 : 128, BN = narrow ? 16 : 128;
+    const bool small = !narrow && (((M + 127) / 128) * ((N + 127) / 128) < 74);      // fewer than half a wave of 128x128 tiles
+    const int BM = narrow ? 256 : (small ? 64 : 128), BN = narrow ? 16 : (small ? 64 : 128);
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int splits = 1;
     if (splitk) {
@@ -168,6 +182,7 @@ static int gemm(cudaStream_t st, const float* A, long long a_ms, long long a_ks,
     }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
     if (narrow) sgemm_kernel<256, 16, 4, 4><<<grid, 256, 0, st>>>(g);
+    else if (small) sgemm_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(g);
     else sgemm_kernel<128, 128, 8, 8><<<grid, 256, 0, st>>>(g);
     SHM_LAUNCH_CHECK();
     return SHM_OK;
@@ -217,63 +232,83 @@ __global__ void swap01_kernel(const float* __restrict__ in, float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Recurrence, forward.  grid = ceil(B / NW), block = 4H threads; thread j <-> (unit u = j>>2, gate g = j&3).
+// Recurrence, forward.  grid = ceil(B / NW), block = 2H threads.  Thread j <-> (unit u = j>>1, pair p = j&1) owns TWO
+// gate rows of unit u -- p=0: (i, f), p=1: (g, o) -- so every broadcast load of h_{t-1} feeds two dot products and the
+// cell update needs one lane exchange (shfl.xor 1).  W_hh stays resident for all T steps: k < KS in shared memory
+// ([k/4][row] float4, conflict-free), k >= KS in registers (H=128: 128 KB smem + 128 registers per thread; H<=64: all
+// of it in registers).
 // ------------------------------------------------------------------------------------------------------------
 template <int H> struct RecCfg {
-    static constexpr int KS = (H == 128) ? 96 : H;     // k range of W_hh kept in shared memory
-    static constexpr int KR = H - KS;                  // k range kept in registers
+    static constexpr int KS = (H == 128) ? 64 : 0;     // forward: k range of W_hh kept in shared memory
+    static constexpr int KR = H - KS;                  // forward: k range kept in registers (x2 rows per thread)
+    static constexpr int MS = (H == 128) ? 128 : 0;    // backward: rows (of the 2H a thread reduces over) kept in shared memory
+    static constexpr int MR = 2 * H - MS;              // backward: rows kept in registers
 };
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
 
 template <int H, int NW>
-__global__ void __launch_bounds__(4 * H, 1)
+__global__ void __launch_bounds__(2 * H)
 lstm_rec_fwd_kernel(const float* __restrict__ w_hh, const float* gx, long long gx_tstride, float* act,
                     float* __restrict__ hs, float* __restrict__ cs, float* __restrict__ hd, const uint8_t* __restrict__ mask,
                     float scale, int T, int B) {
     constexpr int G4 = 4 * H, KS = RecCfg<H>::KS, KR = RecCfg<H>::KR;
     extern __shared__ float4 smem4[];
-    float4* Wt = smem4;                                         // [KS/4][4H]
+    float4* Wt = smem4;                                         // [KS/4][4H]: slot j = row r0 of thread j, slot 2H+j = row r1
     float* hbuf = reinterpret_cast<float*>(Wt + (KS / 4) * G4); // [2][NW][H]
-    const int j = threadIdx.x, g = j & 3, u = j >> 2, n = g * H + u;
-    const int lane_base = (j & 31) & ~3;
-    const float* wrow = w_hh + (size_t)n * H;
-#pragma unroll 4
-    for (int k4 = 0; k4 < KS / 4; ++k4)        // scalar loads: flat parameter offsets are not 16-byte aligned in general (odd Z)
-        Wt[k4 * G4 + j] = make_float4(wrow[4 * k4], wrow[4 * k4 + 1], wrow[4 * k4 + 2], wrow[4 * k4 + 3]);
-    float wreg[KR > 0 ? KR : 1];
+    const int j = threadIdx.x, p = j & 1, u = j >> 1;
+    const int r0 = (2 * p) * H + u, r1 = (2 * p + 1) * H + u;   // reference row order: gate*H + unit, gates i,f,g,o
+    const float* w0 = w_hh + (size_t)r0 * H;
+    const float* w1 = w_hh + (size_t)r1 * H;
+    for (int k4 = 0; k4 < KS / 4; ++k4) {      // scalar loads: flat parameter offsets are not 16-byte aligned in general
+        Wt[k4 * G4 + j] = make_float4(w0[4 * k4], w0[4 * k4 + 1], w0[4 * k4 + 2], w0[4 * k4 + 3]);
+        Wt[k4 * G4 + 2 * H + j] = make_float4(w1[4 * k4], w1[4 * k4 + 1], w1[4 * k4 + 2], w1[4 * k4 + 3]);
+    }
+    float wr0[KR], wr1[KR];
 #pragma unroll
-    for (int i = 0; i < KR; ++i) wreg[i] = wrow[KS + i];
-    for (int i = j; i < 2 * NW * H; i += G4) hbuf[i] = 0.f;
+    for (int i = 0; i < KR; ++i) { wr0[i] = w0[KS + i]; wr1[i] = w1[KS + i]; }
+    for (int i = j; i < 2 * NW * H; i += 2 * H) hbuf[i] = 0.f;
     const int b0 = blockIdx.x * NW;
-    float c[NW], pre[NW];
+    float c[NW], pre0[NW], pre1[NW];
+    unsigned int mk[NW];                        // raw keep-mask byte of the NEXT step (converted only when consumed)
     bool valid[NW];
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
         c[w] = 0.f;
         valid[w] = (b0 + w) < B;
-        pre[w] = valid[w] ? gx[(size_t)(b0 + w) * G4 + n] : 0.f;
-        if (valid[w] && g == 0) { hs[(size_t)(b0 + w) * H + u] = 0.f; cs[(size_t)(b0 + w) * H + u] = 0.f; }
+        pre0[w] = valid[w] ? gx[(size_t)(b0 + w) * G4 + r0] : 0.f;
+        pre1[w] = valid[w] ? gx[(size_t)(b0 + w) * G4 + r1] : 0.f;
+        mk[w] = (mask && valid[w]) ? mask[((size_t)(b0 + w) * T) * H + u] : 1u;
+        if (valid[w] && p == 0) { hs[(size_t)(b0 + w) * H + u] = 0.f; cs[(size_t)(b0 + w) * H + u] = 0.f; }
     }
     __syncthreads();
     for (int t = 0; t < T; ++t) {
-        float acc[NW];
+        float a0[NW], a1[NW];
+        unsigned int mcur[NW];
 #pragma unroll
-        for (int w = 0; w < NW; ++w) acc[w] = pre[w];
-        if (t + 1 < T) {
+        for (int w = 0; w < NW; ++w) { a0[w] = pre0[w]; a1[w] = pre1[w]; mcur[w] = mk[w]; }
+        if (t + 1 < T) {                        // next step's inputs: issued a full step before they are consumed
 #pragma unroll
             for (int w = 0; w < NW; ++w)
-                if (valid[w]) pre[w] = gx[(size_t)(t + 1) * gx_tstride + (size_t)(b0 + w) * G4 + n];
+                if (valid[w]) {
+                    const size_t o = (size_t)(t + 1) * gx_tstride + (size_t)(b0 + w) * G4;
+                    pre0[w] = gx[o + r0];
+                    pre1[w] = gx[o + r1];
+                    if (mask) mk[w] = mask[((size_t)(b0 + w) * T + t + 1) * H + u];
+                }
         }
         const float* hb = hbuf + (t & 1) * NW * H;
-#pragma unroll 8
+#pragma unroll
         for (int k4 = 0; k4 < KS / 4; ++k4) {
-            const float4 w4 = Wt[k4 * G4 + j];
+            const float4 x0 = Wt[k4 * G4 + j];
+            const float4 x1 = Wt[k4 * G4 + 2 * H + j];
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 const float4 h4 = *reinterpret_cast<const float4*>(hb + w * H + 4 * k4);
-                acc[w] = fmaf(w4.x, h4.x, acc[w]); acc[w] = fmaf(w4.y, h4.y, acc[w]);
-                acc[w] = fmaf(w4.z, h4.z, acc[w]); acc[w] = fmaf(w4.w, h4.w, acc[w]);
+                a0[w] = fmaf(x0.x, h4.x, a0[w]); a0[w] = fmaf(x0.y, h4.y, a0[w]);
+                a0[w] = fmaf(x0.z, h4.z, a0[w]); a0[w] = fmaf(x0.w, h4.w, a0[w]);
+                a1[w] = fmaf(x1.x, h4.x, a1[w]); a1[w] = fmaf(x1.y, h4.y, a1[w]);
+                a1[w] = fmaf(x1.z, h4.z, a1[w]); a1[w] = fmaf(x1.w, h4.w, a1[w]);
             }
         }
 #pragma unroll
@@ -281,30 +316,30 @@ lstm_rec_fwd_kernel(const float* __restrict__ w_hh, const float* gx, long long g
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 const float4 h4 = *reinterpret_cast<const float4*>(hb + w * H + KS + i);
-                acc[w] = fmaf(wreg[i], h4.x, acc[w]); acc[w] = fmaf(wreg[i + 1], h4.y, acc[w]);
-                acc[w] = fmaf(wreg[i + 2], h4.z, acc[w]); acc[w] = fmaf(wreg[i + 3], h4.w, acc[w]);
+                a0[w] = fmaf(wr0[i], h4.x, a0[w]); a0[w] = fmaf(wr0[i + 1], h4.y, a0[w]);
+                a0[w] = fmaf(wr0[i + 2], h4.z, a0[w]); a0[w] = fmaf(wr0[i + 3], h4.w, a0[w]);
+                a1[w] = fmaf(wr1[i], h4.x, a1[w]); a1[w] = fmaf(wr1[i + 1], h4.y, a1[w]);
+                a1[w] = fmaf(wr1[i + 2], h4.z, a1[w]); a1[w] = fmaf(wr1[i + 3], h4.w, a1[w]);
             }
         }
         float* hn = hbuf + ((t + 1) & 1) * NW * H;
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
-            const float a = (g == 2) ? tanhf(acc[w]) : sigmoidf_acc(acc[w]);
-            const float gi = __shfl_sync(0xffffffffu, a, lane_base);
-            const float gf = __shfl_sync(0xffffffffu, a, lane_base + 1);
-            const float gg = __shfl_sync(0xffffffffu, a, lane_base + 2);
-            const float go = __shfl_sync(0xffffffffu, a, lane_base + 3);
+            const float v0 = (p == 1) ? tanhf(a0[w]) : sigmoidf_acc(a0[w]);   // p=0: i, p=1: g
+            const float v1 = sigmoidf_acc(a1[w]);                              // p=0: f, p=1: o
+            const float o0 = __shfl_xor_sync(0xffffffffu, v0, 1);
+            const float o1 = __shfl_xor_sync(0xffffffffu, v1, 1);
+            const float gi = p ? o0 : v0, gf = p ? o1 : v1, gg = p ? v0 : o0, go = p ? v1 : o1;
             c[w] = fmaf(gf, c[w], gi * gg);
             const float h = go * tanhf(c[w]);
-            if (g == 0) hn[w * H + u] = h;
+            if (p == 0) hn[w * H + u] = h;
             if (valid[w]) {
                 const size_t tb = (size_t)t * B + (b0 + w);
-                act[tb * G4 + n] = a;
-                if (g == 0) {
-                    const size_t o = ((size_t)(t + 1) * B + (b0 + w)) * H + u;
-                    cs[o] = c[w];
-                    hs[o] = h;
-                    if (hd) hd[tb * H + u] = mask ? h * (mask[((size_t)(b0 + w) * T + t) * H + u] ? scale : 0.f) : h;
-                }
+                act[tb * G4 + r0] = v0;
+                act[tb * G4 + r1] = v1;
+                const size_t o = ((size_t)(t + 1) * B + (b0 + w)) * H + u;
+                if (p == 0) { hs[o] = h; cs[o] = c[w]; }
+                else if (hd) hd[tb * H + u] = mask ? (mcur[w] ? h * scale : 0.f) : h;
             }
         }
         __syncthreads();
@@ -312,115 +347,118 @@ lstm_rec_fwd_kernel(const float* __restrict__ w_hh, const float* gx, long long g
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Recurrence, backward (BPTT).  Phase A (thread <-> (unit, gate)): gate pre-activation gradients of step t;
-// phase B (thread <-> (k, gate block q)): dh_{t-1}[k] += sum_u dG[q*H+u] * W_hh[q*H+u][k] with W_hh resident.
+// Recurrence, backward (BPTT).  Phase A (thread <-> (unit, pair) as in the forward kernel): pre-activation gradients of
+// the thread's two gate rows at step t; phase B (thread <-> (k, half q) with q = tid / H): the partial
+// dh_{t-1}[k] = sum over the 2H gate rows of half q of dG[n] * W_hh[n][k], W_hh^T resident (shared memory + registers).
 // act_dg holds the saved gate activations on entry and the pre-activation gradients dG on exit (in place).
 // ------------------------------------------------------------------------------------------------------------
 template <int H, int NW>
-__global__ void __launch_bounds__(4 * H, 1)
-lstm_rec_bwd_kernel(const float* __restrict__ w_hh, float* __restrict__ act_dg, const float* __restrict__ cs,
+__global__ void __launch_bounds__(2 * H)
+lstm_rec_bwd_kernel(const float* __restrict__ w_hh, float* act_dg, const float* __restrict__ cs,
                     const float* __restrict__ dH, const uint8_t* __restrict__ mask, float scale,
                     const float* __restrict__ dh_last, float* __restrict__ dgsum, int T, int B) {
-    constexpr int G4 = 4 * H, KS = RecCfg<H>::KS, KR = RecCfg<H>::KR;
+    constexpr int G4 = 4 * H, H2 = 2 * H, MS = RecCfg<H>::MS, MR = RecCfg<H>::MR;
     extern __shared__ float4 smem4[];
-    float4* Wb = smem4;                                           // [KS/4][4H]
-    float* dgs = reinterpret_cast<float*>(Wb + (KS / 4) * G4);    // [NW][4H]   (reference row order n = g*H+u)
-    float* red = dgs + NW * G4;                                   // [4][NW][H]
+    float4* Wb = smem4;                                           // [MS/4][2H]
+    float* dgs = reinterpret_cast<float*>(Wb + (MS / 4) * H2);    // [NW][4H]   (reference row order n = gate*H + unit)
+    float* red = dgs + NW * G4;                                   // [2][NW][H]
     const int tid = threadIdx.x;
-    const int g = tid & 3, u = tid >> 2, n = g * H + u;           // phase A role
-    const int q = tid / H, k = tid % H;                           // phase B role
-    const int lane_base = (tid & 31) & ~3;
-#pragma unroll 4
-    for (int u4 = 0; u4 < KS / 4; ++u4) {
-        const float* p = w_hh + (size_t)(q * H + 4 * u4) * H + k;
-        Wb[u4 * G4 + tid] = make_float4(p[0], p[H], p[2 * H], p[3 * H]);
+    const int p = tid & 1, u = tid >> 1;                          // phase A role
+    const int r0 = (2 * p) * H + u, r1 = (2 * p + 1) * H + u;
+    const int q = tid / H, k = tid % H;                           // phase B role: rows [q*2H, (q+1)*2H), column k
+    for (int m4 = 0; m4 < MS / 4; ++m4) {
+        const float* src = w_hh + (size_t)(q * H2 + 4 * m4) * H + k;
+        Wb[m4 * H2 + tid] = make_float4(src[0], src[H], src[2 * H], src[3 * H]);
     }
-    float wreg[KR > 0 ? KR : 1];
+    float wreg[MR];
 #pragma unroll
-    for (int i = 0; i < KR; ++i) wreg[i] = w_hh[(size_t)(q * H + KS + i) * H + k];
-    for (int i = tid; i < 4 * NW * H; i += G4) red[i] = 0.f;
+    for (int i = 0; i < MR; ++i) wreg[i] = w_hh[(size_t)(q * H2 + MS + i) * H + k];
+    for (int i = tid; i < 2 * NW * H; i += H2) red[i] = 0.f;
     const int b0 = blockIdx.x * NW;
-    float dc[NW], gsum[NW], a_n[NW], ct_n[NW], cp_n[NW], dh_n[NW];
+    float dc[NW], gs0[NW], gs1[NW], a0_n[NW], a1_n[NW], ct_n[NW], cp_n[NW], dh_n[NW], dl_n[NW];
+    unsigned int mk_n[NW];
     bool valid[NW];
     auto fetch = [&](int t) {
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
-            if (!valid[w]) { a_n[w] = 0.f; ct_n[w] = 0.f; cp_n[w] = 0.f; dh_n[w] = 0.f; continue; }
+            if (!valid[w]) { a0_n[w] = 0.f; a1_n[w] = 0.f; ct_n[w] = 0.f; cp_n[w] = 0.f; dh_n[w] = 0.f; dl_n[w] = 0.f; mk_n[w] = 1u; continue; }
             const int b = b0 + w;
             const size_t tb = (size_t)t * B + b;
-            a_n[w] = act_dg[tb * G4 + n];
+            a0_n[w] = act_dg[tb * G4 + r0];
+            a1_n[w] = act_dg[tb * G4 + r1];
             ct_n[w] = cs[((size_t)(t + 1) * B + b) * H + u];
             cp_n[w] = cs[tb * H + u];
-            float d = 0.f;
-            if (dH) {
-                d = dH[tb * H + u];
-                if (mask) d *= mask[((size_t)b * T + t) * H + u] ? scale : 0.f;
-            }
-            if (dh_last && t == T - 1) d += dh_last[(size_t)b * H + u];
-            dh_n[w] = d;
+            // raw loads only: nothing here may consume a loaded value, or the prefetch turns into a stall
+            dh_n[w] = dH ? dH[tb * H + u] : 0.f;
+            mk_n[w] = mask ? mask[((size_t)b * T + t) * H + u] : 1u;
+            dl_n[w] = (dh_last && t == T - 1) ? dh_last[(size_t)b * H + u] : 0.f;
         }
     };
 #pragma unroll
-    for (int w = 0; w < NW; ++w) { dc[w] = 0.f; gsum[w] = 0.f; valid[w] = (b0 + w) < B; }
+    for (int w = 0; w < NW; ++w) { dc[w] = 0.f; gs0[w] = 0.f; gs1[w] = 0.f; valid[w] = (b0 + w) < B; }
     fetch(T - 1);
     __syncthreads();
     for (int t = T - 1; t >= 0; --t) {
-        float a[NW], ct[NW], cp[NW], dho[NW];
+        float v0c[NW], v1c[NW], ct[NW], cp[NW], dho[NW];
 #pragma unroll
-        for (int w = 0; w < NW; ++w) { a[w] = a_n[w]; ct[w] = ct_n[w]; cp[w] = cp_n[w]; dho[w] = dh_n[w]; }
+        for (int w = 0; w < NW; ++w) {
+            v0c[w] = a0_n[w]; v1c[w] = a1_n[w]; ct[w] = ct_n[w]; cp[w] = cp_n[w];
+            dho[w] = (mask ? (mk_n[w] ? dh_n[w] * scale : 0.f) : dh_n[w]) + dl_n[w];
+        }
         if (t > 0) fetch(t - 1);
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
-            const float* r = red + w * H + u;
-            const float dh = dho[w] + ((r[0] + r[NW * H]) + (r[2 * NW * H] + r[3 * NW * H]));
-            const float gi = __shfl_sync(0xffffffffu, a[w], lane_base);
-            const float gf = __shfl_sync(0xffffffffu, a[w], lane_base + 1);
-            const float gg = __shfl_sync(0xffffffffu, a[w], lane_base + 2);
-            const float go = __shfl_sync(0xffffffffu, a[w], lane_base + 3);
+            const float dh = dho[w] + (red[w * H + u] + red[(NW + w) * H + u]);
+            const float o0 = __shfl_xor_sync(0xffffffffu, v0c[w], 1);
+            const float o1 = __shfl_xor_sync(0xffffffffu, v1c[w], 1);
+            const float gi = p ? o0 : v0c[w], gf = p ? o1 : v1c[w], gg = p ? v0c[w] : o0, go = p ? v1c[w] : o1;
             const float tc = tanhf(ct[w]);
             const float dct = fmaf(dh * go, 1.f - tc * tc, dc[w]);
             dc[w] = dct * gf;
-            float v;
-            if (g == 0) v = dct * gg * gi * (1.f - gi);
-            else if (g == 1) v = dct * cp[w] * gf * (1.f - gf);
-            else if (g == 2) v = dct * gi * (1.f - gg * gg);
-            else v = dh * tc * go * (1.f - go);
-            if (!valid[w]) v = 0.f;
-            dgs[w * G4 + n] = v;
-            gsum[w] += v;
-            if (valid[w]) act_dg[((size_t)t * B + b0 + w) * G4 + n] = v;
+            float g0, g1;
+            if (p == 0) { g0 = dct * gg * gi * (1.f - gi); g1 = dct * cp[w] * gf * (1.f - gf); }      // d pre-act of i, f
+            else { g0 = dct * gi * (1.f - gg * gg); g1 = dh * tc * go * (1.f - go); }                // d pre-act of g, o
+            if (!valid[w]) { g0 = 0.f; g1 = 0.f; }
+            dgs[w * G4 + r0] = g0;
+            dgs[w * G4 + r1] = g1;
+            gs0[w] += g0; gs1[w] += g1;
+            if (valid[w]) {
+                const size_t tb = (size_t)t * B + b0 + w;
+                act_dg[tb * G4 + r0] = g0;
+                act_dg[tb * G4 + r1] = g1;
+            }
         }
         __syncthreads();
-        float p[NW];
+        float acc[NW];
 #pragma unroll
-        for (int w = 0; w < NW; ++w) p[w] = 0.f;
-#pragma unroll 8
-        for (int u4 = 0; u4 < KS / 4; ++u4) {
-            const float4 w4 = Wb[u4 * G4 + tid];
+        for (int w = 0; w < NW; ++w) acc[w] = 0.f;
+#pragma unroll
+        for (int m4 = 0; m4 < MS / 4; ++m4) {
+            const float4 w4 = Wb[m4 * H2 + tid];
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
-                const float4 d4 = *reinterpret_cast<const float4*>(dgs + w * G4 + q * H + 4 * u4);
-                p[w] = fmaf(w4.x, d4.x, p[w]); p[w] = fmaf(w4.y, d4.y, p[w]);
-                p[w] = fmaf(w4.z, d4.z, p[w]); p[w] = fmaf(w4.w, d4.w, p[w]);
+                const float4 d4 = *reinterpret_cast<const float4*>(dgs + w * G4 + q * H2 + 4 * m4);
+                acc[w] = fmaf(w4.x, d4.x, acc[w]); acc[w] = fmaf(w4.y, d4.y, acc[w]);
+                acc[w] = fmaf(w4.z, d4.z, acc[w]); acc[w] = fmaf(w4.w, d4.w, acc[w]);
             }
         }
 #pragma unroll
-        for (int i = 0; i < KR; i += 4) {
+        for (int i = 0; i < MR; i += 4) {
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
-                const float4 d4 = *reinterpret_cast<const float4*>(dgs + w * G4 + q * H + KS + i);
-                p[w] = fmaf(wreg[i], d4.x, p[w]); p[w] = fmaf(wreg[i + 1], d4.y, p[w]);
-                p[w] = fmaf(wreg[i + 2], d4.z, p[w]); p[w] = fmaf(wreg[i + 3], d4.w, p[w]);
+                const float4 d4 = *reinterpret_cast<const float4*>(dgs + w * G4 + q * H2 + MS + i);
+                acc[w] = fmaf(wreg[i], d4.x, acc[w]); acc[w] = fmaf(wreg[i + 1], d4.y, acc[w]);
+                acc[w] = fmaf(wreg[i + 2], d4.z, acc[w]); acc[w] = fmaf(wreg[i + 3], d4.w, acc[w]);
             }
         }
 #pragma unroll
-        for (int w = 0; w < NW; ++w) red[(q * NW + w) * H + k] = p[w];
+        for (int w = 0; w < NW; ++w) red[(q * NW + w) * H + k] = acc[w];
         __syncthreads();
     }
     if (dgsum) {
 #pragma unroll
         for (int w = 0; w < NW; ++w)
-            if (valid[w]) dgsum[(size_t)(b0 + w) * G4 + n] = gsum[w];
+            if (valid[w]) { dgsum[(size_t)(b0 + w) * G4 + r0] = gs0[w]; dgsum[(size_t)(b0 + w) * G4 + r1] = gs1[w]; }
     }
 }
 
@@ -641,10 +679,11 @@ static int launch_rec_fwd(cudaStream_t st, int nsm, const float* w_hh, const flo
     const int nw = B <= nsm ? 1 : (B <= 2 * nsm ? 2 : 4);
     const size_t smem = (size_t)(KS / 4) * 4 * H * sizeof(float4) + (size_t)2 * nw * H * sizeof(float);
     const int grid = (B + nw - 1) / nw;
+    constexpr int kThreads = 2 * H;
 #define SHM_REC_FWD(NW)                                                                                                         \
     do {                                                                                                                        \
         SHM_CUDA(cudaFuncSetAttribute(lstm_rec_fwd_kernel<H, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-        lstm_rec_fwd_kernel<H, NW><<<grid, 4 * H, smem, st>>>(w_hh, gx, tstride, act, hs, cs, hd, mask, scale, T, B);           \
+        lstm_rec_fwd_kernel<H, NW><<<grid, kThreads, smem, st>>>(w_hh, gx, tstride, act, hs, cs, hd, mask, scale, T, B);           \
     } while (0)
     if (nw == 1) SHM_REC_FWD(1); else if (nw == 2) SHM_REC_FWD(2); else SHM_REC_FWD(4);
 #undef SHM_REC_FWD
@@ -655,14 +694,15 @@ static int launch_rec_fwd(cudaStream_t st, int nsm, const float* w_hh, const flo
 template <int H>
 static int launch_rec_bwd(cudaStream_t st, int nsm, const float* w_hh, float* act_dg, const float* cs, const float* dH,
                           const uint8_t* mask, float scale, const float* dh_last, float* dgsum, int T, int B) {
-    constexpr int KS = RecCfg<H>::KS;
+    constexpr int MS = RecCfg<H>::MS;
     const int nw = B <= nsm ? 1 : (B <= 2 * nsm ? 2 : 4);
-    const size_t smem = (size_t)(KS / 4) * 4 * H * sizeof(float4) + (size_t)(nw * 4 * H + 4 * nw * H) * sizeof(float);
+    const size_t smem = (size_t)(MS / 4) * 2 * H * sizeof(float4) + (size_t)(nw * 4 * H + 2 * nw * H) * sizeof(float);
     const int grid = (B + nw - 1) / nw;
+    constexpr int kThreads = 2 * H;
 #define SHM_REC_BWD(NW)                                                                                                         \
     do {                                                                                                                        \
         SHM_CUDA(cudaFuncSetAttribute(lstm_rec_bwd_kernel<H, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-        lstm_rec_bwd_kernel<H, NW><<<grid, 4 * H, smem, st>>>(w_hh, act_dg, cs, dH, mask, scale, dh_last, dgsum, T, B);         \
+        lstm_rec_bwd_kernel<H, NW><<<grid, kThreads, smem, st>>>(w_hh, act_dg, cs, dH, mask, scale, dh_last, dgsum, T, B);         \
     } while (0)
     if (nw == 1) SHM_REC_BWD(1); else if (nw == 2) SHM_REC_BWD(2); else SHM_REC_BWD(4);
 #undef SHM_REC_BWD
