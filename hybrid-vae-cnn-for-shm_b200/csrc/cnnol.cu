@@ -12,9 +12,13 @@
 // thread fetches 4 output channels per 16-byte read-only load (L1/L2 resident, shared by all CTAs).
 #include <new>
 #include "common.cuh"
+#include "cnnol_tc.cuh"
 
 struct shm_cnnol {
     int device;
+    int engine;                 // SHM_ENGINE_FP32 or SHM_ENGINE_TC_BF16X3 (tensor cores, 3-pass fp16 split)
+    shm::CnnOlTc tc;
+    const float* raw_w[4];      // staged reference-layout conv weights inside `raw`
     float* buf;
     float* raw;
     size_t o_w[4], o_b[4], o_gw[4], o_gb[4], o_fc1t, o_fc1b, o_fc2w, o_fc2b, total, raw_total;
@@ -254,6 +258,7 @@ static int cnnol_upload(shm_cnnol* h, const shm_cnnol_weights* w, cudaStream_t s
         float* d;
         const size_t nw = (size_t)OL_COUT[b] * OL_CIN[b] * OL_KT[b] * 3;
         if ((rc = stage(w->conv_w[b], nw, &d))) return rc;
+        h->raw_w[b] = d;
         cnnol_pack_conv_kernel<<<148, 256, 0, st>>>(d, OL_COUT[b], OL_CIN[b], OL_KT[b], h->buf + h->o_w[b]);
         SHM_LAUNCH_CHECK();
         if ((rc = direct(h->o_b[b], w->conv_b[b], OL_COUT[b]))) return rc;
@@ -268,7 +273,7 @@ static int cnnol_upload(shm_cnnol* h, const shm_cnnol_weights* w, cudaStream_t s
     if ((rc = direct(h->o_fc2w, w->fc2_w, 256))) return rc;
     if ((rc = direct(h->o_fc2b, w->fc2_b, 2))) return rc;
     h->gn_eps = w->gn_eps > 0.f ? w->gn_eps : 1e-5f;
-    return SHM_OK;
+    return cnnol_tc_pack(&h->tc, h->raw_w, st);
 }
 
 static constexpr size_t kCnnOlSmem = (size_t)(OL_PLANE_IN + OL_PLANE_OUT) * sizeof(float);
@@ -302,7 +307,9 @@ extern "C" int shm_cnnol_create(shm_cnnol** out, const shm_cnnol_weights* w, int
         cudaSetDevice(prev);
         return SHM_ERR_NOMEM;
     }
-    rc = cnnol_upload(h, w, 0);
+    h->engine = SHM_ENGINE_TC_BF16X3;
+    rc = cnnol_tc_init(&h->tc, device);
+    if (rc == SHM_OK) rc = cnnol_upload(h, w, 0);
     if (rc == SHM_OK && cudaStreamSynchronize(0) != cudaSuccess) { set_cuda_error(cudaGetLastError(), "cnnol create"); rc = SHM_ERR_CUDA; }
     if (rc == SHM_OK && cudaFuncSetAttribute(cnnol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCnnOlSmem) != cudaSuccess) {
         set_cuda_error(cudaGetLastError(), "cudaFuncSetAttribute(cnnol)");
@@ -323,6 +330,7 @@ extern "C" int shm_cnnol_destroy(shm_cnnol* h) {
     if (!h) return SHM_OK;
     if (h->buf) cudaFree(h->buf);
     if (h->raw) cudaFree(h->raw);
+    cnnol_tc_free(&h->tc);
     delete h;
     return SHM_OK;
 }
@@ -341,9 +349,22 @@ extern "C" int shm_cnnol_forward(shm_cnnol* h, const shm_window_src* src_host, c
     }
     P.fc1t = h->buf + h->o_fc1t; P.fc1b = h->buf + h->o_fc1b; P.fc2w = h->buf + h->o_fc2w; P.fc2b = h->buf + h->o_fc2b;
     P.gn_eps = h->gn_eps;
+    if (h->engine == SHM_ENGINE_TC_BF16X3)
+        return cnnol_tc_forward(&h->tc, h->raw_w[0], P.b, P.gw, P.gb, P.fc1t, P.fc1b, P.fc2w, P.fc2b, h->gn_eps, src, idx, n_dev, n,
+                                logits, prob, static_cast<cudaStream_t>(stream));
     const int sms = device_sm_count(h->device);
     const int grid = (int)min((long long)n, (long long)sms * 8);
     cnnol_kernel<<<grid, OL_THREADS, kCnnOlSmem, static_cast<cudaStream_t>(stream)>>>(P, src, idx, n_dev, n, logits, prob);
     SHM_LAUNCH_CHECK();
     return SHM_OK;
 }
+
+extern "C" int shm_cnnol_set_engine(shm_cnnol* h, int engine) {
+    if (!h) return SHM_ERR_ARG;
+    if (engine == SHM_ENGINE_AUTO) engine = SHM_ENGINE_TC_BF16X3;
+    if (engine != SHM_ENGINE_FP32 && engine != SHM_ENGINE_TC_BF16X3) return SHM_ERR_UNSUPPORTED;
+    h->engine = engine;
+    return SHM_OK;
+}
+
+extern "C" int shm_cnnol_engine(const shm_cnnol* h) { return h ? h->engine : SHM_ERR_ARG; }

@@ -86,6 +86,8 @@ SIGNATURES = {
     "shm_cnnol_update_weights": (C.c_int, [_vp, C.POINTER(CnnOlWeights), _vp]),
     "shm_cnnol_destroy": (C.c_int, [_vp]),
     "shm_cnnol_forward": (C.c_int, [_vp, C.POINTER(WindowSrc), _vp, _vp, C.c_int64, _vp, _vp, _vp]),
+    "shm_cnnol_set_engine": (C.c_int, [_vp, C.c_int]),
+    "shm_cnnol_engine": (C.c_int, [_vp]),
     "shm_stitch_segment_rmse": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _vp, _vp, _vp,
                                           C.c_int32, _vp, _vp, _vp]),
     "shm_percentile_workspace_bytes": (C.c_int64, [C.c_int64]),

@@ -321,7 +321,7 @@ class CnnOpenLab:
 
     BLOCKS = (0, 2, 4, 6)
 
-    def __init__(self, state: dict, device: torch.device, gn_eps: float = 1e-5):
+    def __init__(self, state: dict, device: torch.device, gn_eps: float = 1e-5, engine: int = ENGINE_AUTO):
         self._lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -332,6 +332,8 @@ class CnnOpenLab:
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         check(self._lib.shm_cnnol_create(C.byref(h), C.byref(w), dev_index), "shm_cnnol_create")
         self._h = h
+        check(self._lib.shm_cnnol_set_engine(h, int(engine)), "shm_cnnol_set_engine")
+        self.engine = self._lib.shm_cnnol_engine(h)       # ENGINE_TC_BF16X3 (default) or ENGINE_FP32
 
     def _weights_struct(self, state):
         keep = []

@@ -198,12 +198,16 @@ def test_cnn4dof_vs_golden(cuda_dev, golden_dir):
         assert np.allclose(m(to_dev(xin, cuda_dev)).cpu().numpy(), g["logits"], rtol=REL_TOL, atol=LOGIT_ABS)
 
 
-def test_cnnol_vs_golden(cuda_dev, golden_dir):
+@pytest.mark.parametrize("engine", engines())
+def test_cnnol_vs_golden(cuda_dev, golden_dir, engine):
     g = np.load(golden_dir / "synth_cnnol.npz")
     sd = synth.cnnol_weights(seed=int(g["seed"]))
     x = synth.windows(int(g["N"]), 200, 4, seed=31, amp=1.5)
-    cnn = ops.CnnOpenLab(sd, cuda_dev)
+    cnn = ops.CnnOpenLab(sd, cuda_dev, engine=engine)
+    assert cnn.engine == engine
     logits, prob = cnn.forward(ops.WindowSource(to_dev(x, cuda_dev), 200), want_prob=True)
+    err = np.max(np.abs(logits.cpu().numpy() - g["logits"]) / np.maximum(np.abs(g["logits"]), LOGIT_ABS / REL_TOL))
+    print(f"cnnol engine={engine}: logits err (rel, floor {LOGIT_ABS / REL_TOL:g}) {err:.2e}")
     assert np.allclose(logits.cpu().numpy(), g["logits"], rtol=REL_TOL, atol=LOGIT_ABS)
     _, p_o = O.cnnol_decision(g["logits"], 0.5)
     assert np.allclose(prob.cpu().numpy(), p_o, atol=1e-5)
@@ -214,11 +218,39 @@ def test_cnnol_vs_golden(cuda_dev, golden_dir):
         assert np.allclose(m(to_dev(x[:, None], cuda_dev)).cpu().numpy(), g["logits"], rtol=REL_TOL, atol=LOGIT_ABS)
 
 
-def test_openlab_hybrid_real_windows(cuda_dev, golden_dir):
+@pytest.mark.parametrize("engine", engines())
+def test_cnnol_ragged_idx_and_device_count(cuda_dev, engine):
+    """Flagged-subset call pattern of stage2_predict_cnn (10_test_hybrid_pipeline.py:265-302): idx list + device-side
+    count, window counts that are not a multiple of any tile shape, NaN-bearing raw windows; against the oracle."""
+    sd = synth.cnnol_weights(seed=77)
+    rng = np.random.Generator(np.random.PCG64(78))
+    N = 333
+    x = synth.windows(N, 200, 4, seed=79, amp=2.0)
+    x[5, 10:30, 2] = np.nan
+    x[200, :, 0] = np.inf
+    mu, sd_ = synth.stats(4, seed=80)
+    idx = np.sort(rng.choice(N, size=101, replace=False)).astype(np.int32)
+    cnn = ops.CnnOpenLab(sd, cuda_dev, engine=engine)
+    src = ops.WindowSource(to_dev(x, cuda_dev), 200, mean=mu, std=sd_, clip=10.0, nan_to_zero=True)
+    count = torch.tensor([77], dtype=torch.int32, device=cuda_dev)
+    logits, prob = cnn.forward(src, n=101, idx=to_dev(idx, cuda_dev), n_dev=count, want_prob=True)
+    xs = O.standardize_openlab(x[idx[:77]], mu, sd_, 10.0)
+    ref = O.cnnol_forward(sd, xs[:, None].astype(np.float32))
+    assert np.allclose(logits[:77].cpu().numpy(), ref, rtol=REL_TOL, atol=LOGIT_ABS)
+    _, p_o = O.cnnol_decision(ref, 0.5)
+    assert np.allclose(prob[:77].cpu().numpy(), p_o, atol=1e-5)
+    for n in (1, 3, 17):                                  # tiny batches: partial groups in every block
+        l2 = cnn.forward(src, n=n)
+        xs = O.standardize_openlab(x[:n], mu, sd_, 10.0)
+        assert np.allclose(l2.cpu().numpy(), O.cnnol_forward(sd, xs[:, None].astype(np.float32)), rtol=REL_TOL, atol=LOGIT_ABS)
+
+
+@pytest.mark.parametrize("engine", engines())
+def test_openlab_hybrid_real_windows(cuda_dev, golden_dir, engine):
     g = np.load(golden_dir / "openlab_real_windows.npz")
     seed = int(g["seed"])
     vae = ops.VaeScorer(synth.stage_vae_weights("openlab", seed=seed, scale=2.0), cuda_dev)
-    cnn = ops.CnnOpenLab(synth.cnnol_weights(seed=seed), cuda_dev)
+    cnn = ops.CnnOpenLab(synth.cnnol_weights(seed=seed), cuda_dev, engine=engine)
     N = g["X_clean"].shape[0]
     eps = synth.eps(N, 8, seed=seed)
     Xc, Xr = to_dev(g["X_clean"], cuda_dev), to_dev(g["X_raw"], cuda_dev)
