@@ -505,7 +505,8 @@ def run_openlab(a):
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if vae.engine == ops.ENGINE_FP32 else "bf16x3->f32", "data": "synthetic",
             "config": {"workload": "openlab_hybrid", "windows_per_gpu": N, "T": 200, "stride": 20, "D_gate": 3, "D_raw": 4, "H": 64, "Z": 8, "L": 1,
-                       "engine": eng, "gate_threshold": f"P{pct:g} of 2000 calibration windows", "flagged_per_gpu": n_flag, "cnn_threshold": 0.5,
+                       "engine": eng, "cnn_engine": {ops.ENGINE_FP32: "fp32", ops.ENGINE_TC_BF16X3: "tc_f16x3 (tcgen05 implicit GEMM)"}[cnn.engine],
+                       "gate_threshold": f"P{pct:g} of 2000 calibration windows", "flagged_per_gpu": n_flag, "cnn_threshold": 0.5,
                        "input": "raw 4-channel series with NaN runs, stride 20; gather+standardise fused into scorer and CNN",
                        "l2": "flushed between timed steps (512 MiB memset)", "parallelism": f"window-range shards x{world}, no collective"},
             "clocks": clocks,
