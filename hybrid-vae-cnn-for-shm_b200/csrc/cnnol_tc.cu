@@ -45,11 +45,18 @@ template <int L> struct OlDer {
     static constexpr int NCC = G::CIN / 16;
     static constexpr int A_IMG = R * 32;                   // bytes: R rows x 16 fp16
     static constexpr int A_STAGE = 6 * A_IMG;              // 3 df shifts x {hi, lo}
-    static constexpr int B_STAGE = G::NOUT * 64;           // {hi, lo} x [NOUT x 16] fp16
+    static constexpr int TG = (G::NOUT <= 64) ? 3 : 1;     // taps per weight stage (small-N MMAs are short: fewer barrier round trips)
+    static constexpr int B_TAP = G::NOUT * 64;             // {hi, lo} x [NOUT x 16] fp16 of one tap
+    static constexpr int B_STAGE = TG * B_TAP;
     static constexpr int NB = 4;                           // weight ring stages
-    static constexpr int SMEM = 2 * A_STAGE + NB * B_STAGE + 256;
-    static constexpr int TCOLS = (2 * G::NOUT <= 128) ? 128 : ((2 * G::NOUT <= 256) ? 256 : 512);
+    static constexpr int NACC = (4 * G::NOUT <= 512) ? 2 : 1;   // accumulator sets (pair = 2*NOUT columns): double buffered when TMEM allows
+    static constexpr int OFF_BAR = 2 * A_STAGE + NB * B_STAGE;
+    static constexpr int OFF_BIAS = OFF_BAR + 256;         // fp32 bias[NOUT]
+    static constexpr int OFF_RED = OFF_BIAS + G::NOUT * 4; // fp64 [4 warps][8 windows][16] GroupNorm partials
+    static constexpr int SMEM = OFF_RED + 4 * 8 * 16 * 8;
+    static constexpr int TCOLS = (2 * NACC * G::NOUT <= 128) ? 128 : ((2 * NACC * G::NOUT <= 256) ? 256 : 512);
     static_assert(SMEM <= 232448, "shared memory budget");
+    static_assert((G::KT * 3) % TG == 0, "tap groups");
 };
 
 __device__ __forceinline__ float silu_acc(float x) { return x / (1.0f + expf(-x)); }
@@ -245,7 +252,7 @@ struct OlGemmArgs {
 };
 
 template <int L> struct OlBars {
-    uint64_t a_full[2], a_empty[2], b_full[OlDer<L>::NB], b_empty[OlDer<L>::NB], acc_full, acc_empty;
+    uint64_t a_full[2], a_empty[2], b_full[OlDer<L>::NB], b_empty[OlDer<L>::NB], acc_full[2], acc_empty[2];
 };
 
 template <int L>
@@ -257,8 +264,10 @@ __global__ void __launch_bounds__(224, 1) ol_conv_gemm_kernel(const OlGemmArgs a
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* As = smem;
     unsigned char* Bs = smem + 2 * D::A_STAGE;
-    OlBars<L>* bars = reinterpret_cast<OlBars<L>*>(smem + 2 * D::A_STAGE + D::NB * D::B_STAGE);
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + 2 * D::A_STAGE + D::NB * D::B_STAGE + 192);
+    OlBars<L>* bars = reinterpret_cast<OlBars<L>*>(smem + D::OFF_BAR);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + D::OFF_BAR + 192);
+    float* bias_s = reinterpret_cast<float*>(smem + D::OFF_BIAS);
+    double* red_s = reinterpret_cast<double*>(smem + D::OFF_RED);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long n_eff = eff_windows(a.n_total, a.n_dev, a.base, a.n_chunk);
     const long long groups = (n_eff + D::WPT - 1) / D::WPT;
@@ -267,10 +276,10 @@ __global__ void __launch_bounds__(224, 1) ol_conv_gemm_kernel(const OlGemmArgs a
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
         for (int i = 0; i < D::NB; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
-        mbar_init(&bars->acc_full, 1);
-        mbar_init(&bars->acc_empty, 4);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
         fence_mbar_init();
     }
+    for (int i = tid; i < NOUT; i += 224) bias_s[i] = __ldg(a.bias + i);
     if (warp == 6) tmem_alloc(tmem_holder, D::TCOLS);
     tc_fence_before_sync();
     __syncthreads();
@@ -297,7 +306,7 @@ __global__ void __launch_bounds__(224, 1) ol_conv_gemm_kernel(const OlGemmArgs a
         if (lane == 0) {
             uint32_t it = 0;
             for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-                for (int st = 0; st < D::NCC * NTAP; ++st, ++it) {
+                for (int st = 0; st < D::NCC * NTAP / D::TG; ++st, ++it) {
                     const uint32_t s = it % D::NB;
                     mbar_wait(&bars->b_empty[s], ((it / D::NB) & 1) ^ 1);
                     mbar_arrive_expect_tx(&bars->b_full[s], (uint32_t)D::B_STAGE);
@@ -310,31 +319,36 @@ __global__ void __launch_bounds__(224, 1) ol_conv_gemm_kernel(const OlGemmArgs a
         const uint32_t as_a = smem_u32(As), bs_a = smem_u32(Bs);
         uint32_t a_it = 0, b_it = 0, n_item = 0;
         for (long long item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
-            mbar_wait(&bars->acc_empty, (n_item & 1) ^ 1);         // epilogue drained the previous pair
+            const uint32_t ab_set = n_item % D::NACC;                      // accumulator set of this pair
+            mbar_wait(&bars->acc_empty[ab_set], ((n_item / D::NACC) & 1) ^ 1);   // epilogue drained the pair that used it last
             tc_fence_after_sync();
             for (int cc = 0; cc < D::NCC; ++cc, ++a_it) {
                 const uint32_t sa = a_it & 1;
                 mbar_wait(&bars->a_full[sa], (a_it >> 1) & 1);
                 tc_fence_after_sync();
-                for (int tap = 0; tap < NTAP; ++tap, ++b_it) {
+                for (int tg = 0; tg < NTAP / D::TG; ++tg, ++b_it) {
                     const uint32_t sb = b_it % D::NB;
                     mbar_wait(&bars->b_full[sb], (b_it / D::NB) & 1);
                     tc_fence_after_sync();
                     if (elect_one()) {
-                        const int dt = tap / 3, df = tap - dt * 3;
-                        const uint32_t bb = bs_a + sb * D::B_STAGE;
-                        const uint64_t b_hi = make_smem_desc(bb, NOUT * 16, 128);
-                        const uint64_t b_lo = make_smem_desc(bb + NOUT * 32, NOUT * 16, 128);
-                        const uint32_t ab = as_a + sa * D::A_STAGE + (uint32_t)(df * 2) * D::A_IMG;
 #pragma unroll
-                        for (int tile = 0; tile < 2; ++tile) {
-                            const uint32_t roff = (uint32_t)((dt + tile * D::HT) * RPH / 8) * 128u;
-                            const uint64_t a_hi = make_smem_desc(ab + roff, D::R * 16, 128);
-                            const uint64_t a_lo = make_smem_desc(ab + D::A_IMG + roff, D::R * 16, 128);
-                            const uint32_t acc = tbase + (uint32_t)(tile * NOUT);
-                            mma_ss(acc, a_hi, b_hi, IDESC, (cc | tap) ? 1u : 0u);
-                            mma_ss(acc, a_lo, b_hi, IDESC, 1u);
-                            mma_ss(acc, a_hi, b_lo, IDESC, 1u);
+                        for (int tq = 0; tq < D::TG; ++tq) {
+                            const int tap = tg * D::TG + tq;
+                            const int dt = tap / 3, df = tap - dt * 3;
+                            const uint32_t bb = bs_a + sb * D::B_STAGE + tq * D::B_TAP;
+                            const uint64_t b_hi = make_smem_desc(bb, NOUT * 16, 128);
+                            const uint64_t b_lo = make_smem_desc(bb + NOUT * 32, NOUT * 16, 128);
+                            const uint32_t ab = as_a + sa * D::A_STAGE + (uint32_t)(df * 2) * D::A_IMG;
+#pragma unroll
+                            for (int tile = 0; tile < 2; ++tile) {
+                                const uint32_t roff = (uint32_t)((dt + tile * D::HT) * RPH / 8) * 128u;
+                                const uint64_t a_hi = make_smem_desc(ab + roff, D::R * 16, 128);
+                                const uint64_t a_lo = make_smem_desc(ab + D::A_IMG + roff, D::R * 16, 128);
+                                const uint32_t acc = tbase + (uint32_t)((ab_set * 2 + tile) * NOUT);
+                                mma_ss(acc, a_hi, b_hi, IDESC, (cc | tap) ? 1u : 0u);
+                                mma_ss(acc, a_lo, b_hi, IDESC, 1u);
+                                mma_ss(acc, a_hi, b_lo, IDESC, 1u);
+                            }
                         }
                         mma_commit(&bars->b_empty[sb]);
                     }
@@ -343,61 +357,86 @@ __global__ void __launch_bounds__(224, 1) ol_conv_gemm_kernel(const OlGemmArgs a
                 if (elect_one()) mma_commit(&bars->a_empty[sa]);
                 __syncwarp();
             }
-            if (elect_one()) mma_commit(&bars->acc_full);
+            if (elect_one()) mma_commit(&bars->acc_full[ab_set]);
             __syncwarp();
         }
     } else if (warp < 4) {                             // ---- epilogue: thread = accumulator row
         constexpr int GS = NOUT / 8;                   // channels per GroupNorm group (8, 16, 32)
         constexpr int GPC = 32 / GS;                   // groups per 32-column chunk (4, 2, 1)
+        constexpr int WW = D::WPT < 8 ? D::WPT : 8;    // windows covered by one warp
         const int row = warp * 32 + lane;
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
         const float inv = __ldg(a.wsc + 1);
+        const int wi = (row % RPH) >> 2, w = row & 3;
         uint32_t n_item = 0;
         for (long long item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
             const long long g = item / D::NPAIR;
             const int p = (int)(item - g * D::NPAIR);
-            mbar_wait(&bars->acc_full, n_item & 1);
+            const uint32_t ab_set = n_item % D::NACC;
+            const long long win = g * D::WPT + wi;
+            float gs[8], gq[8];                        // this row's GroupNorm partials over both tiles (same window)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { gs[i] = 0.f; gq[i] = 0.f; }
+            mbar_wait(&bars->acc_full[ab_set], (n_item / D::NACC) & 1);
             tc_fence_after_sync();
 #pragma unroll 1
             for (int tile = 0; tile < 2; ++tile) {
-                const int hl = tile * D::HT + row / RPH;
-                const int wi = (row % RPH) >> 2, w = row & 3;
-                const int h = p * D::PH + hl;
-                const long long win = g * D::WPT + wi;
+                const int h = p * D::PH + tile * D::HT + row / RPH;
                 const bool valid = h < HIN && win < n_eff;
                 float* orow = a.out + (((size_t)(valid ? win : 0) * HIN + (valid ? h : 0)) * 4 + w) * NOUT;
-#pragma unroll 1
+#pragma unroll
                 for (int c0 = 0; c0 < NOUT; c0 += 32) {
                     uint32_t v[32];
-                    tmem_ld32(tbase + lane_base + (uint32_t)(tile * NOUT + c0), v);
+                    tmem_ld32(tbase + lane_base + (uint32_t)((ab_set * 2 + tile) * NOUT + c0), v);
                     tmem_ld_wait();
                     float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), inv, __ldg(a.bias + c0 + j));
+                    for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), inv, bias_s[c0 + j]);
                     if (valid) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q)
                             *reinterpret_cast<float4*>(orow + c0 + 4 * q) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-                    }
 #pragma unroll
-                    for (int gg = 0; gg < GPC; ++gg) {
-                        float s = 0.f, q2 = 0.f;
+                        for (int gg = 0; gg < GPC; ++gg) {
+                            float s1 = 0.f, q2 = 0.f;
 #pragma unroll
-                        for (int j = 0; j < GS && j < 32; ++j) { const float x = f[gg * GS + j]; s += x; q2 = fmaf(x, x, q2); }
-                        if (!valid) { s = 0.f; q2 = 0.f; }
-                        s += __shfl_xor_sync(0xffffffffu, s, 1); q2 += __shfl_xor_sync(0xffffffffu, q2, 1);
-                        s += __shfl_xor_sync(0xffffffffu, s, 2); q2 += __shfl_xor_sync(0xffffffffu, q2, 2);
-                        if (valid && w == 0) {
-                            const int grp = (c0 + gg * GS) / GS;
-                            atomicAdd(a.stats + (size_t)win * 16 + 2 * grp, (double)s);
-                            atomicAdd(a.stats + (size_t)win * 16 + 2 * grp + 1, (double)q2);
+                            for (int j = 0; j < GS && j < 32; ++j) { const float x = f[gg * GS + j]; s1 += x; q2 = fmaf(x, x, q2); }
+                            gs[c0 / GS + gg] += s1;
+                            gq[c0 / GS + gg] += q2;
                         }
                     }
                 }
             }
+            // accumulators are in registers: hand the TMEM set back before the reduction
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->acc_empty);
+            if (lane == 0) mbar_arrive(&bars->acc_empty[ab_set]);
+            // GroupNorm statistics: reduce over the 4 sensor columns (and the 2 time steps a warp holds when RPH = 16),
+            // then across the warps through shared memory in a fixed order; one fp64 atomic per (window, group, stat)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                gs[i] += __shfl_xor_sync(0xffffffffu, gs[i], 1); gq[i] += __shfl_xor_sync(0xffffffffu, gq[i], 1);
+                gs[i] += __shfl_xor_sync(0xffffffffu, gs[i], 2); gq[i] += __shfl_xor_sync(0xffffffffu, gq[i], 2);
+                if (RPH == 16) { gs[i] += __shfl_xor_sync(0xffffffffu, gs[i], 16); gq[i] += __shfl_xor_sync(0xffffffffu, gq[i], 16); }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");            // previous item's partials have been consumed
+            if (w == 0 && (RPH != 16 || lane < 16)) {
+                double* dst = red_s + ((size_t)warp * 8 + (wi % WW)) * 16;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { dst[2 * i] = (double)gs[i]; dst[2 * i + 1] = (double)gq[i]; }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = row; i < D::WPT * 16; i += 128) {
+                const int wq = i >> 4, st = i & 15;                    // window of the group, (group, stat) slot
+                const long long wn = g * D::WPT + wq;
+                if (wn < n_eff) {
+                    double tot;
+                    if (D::WPT <= 8) tot = (red_s[(0 * 8 + wq) * 16 + st] + red_s[(1 * 8 + wq) * 16 + st]) +
+                                           (red_s[(2 * 8 + wq) * 16 + st] + red_s[(3 * 8 + wq) * 16 + st]);
+                    else tot = red_s[(((wq >> 3) + 0) * 8 + (wq & 7)) * 16 + st] + red_s[(((wq >> 3) + 2) * 8 + (wq & 7)) * 16 + st];
+                    atomicAdd(a.stats + (size_t)wn * 16 + st, tot);
+                }
+            }
         }
     }
     tc_fence_before_sync();
