@@ -31,10 +31,13 @@ constexpr int TCM = 128;                       // windows per tile (UMMA M)
 constexpr int TC_NST = 5;                      // weight ring stages
 constexpr int TC_STAGE = 128 * 64 * 2;         // bytes per stage: [128 N-rows x 64 K] bf16
 constexpr int TC_XSTAGE = 128 * 16 * 2;        // [128 x 16] bf16 (window-input tiles)
-constexpr int TC_WARP_AUX0 = 8;               // warps 8-11: window staging (encoder input) / output Linear + error (decoder)
-constexpr int TC_WARP_PROD = 12, TC_WARP_MMA = 13;
-constexpr int TC_THREADS = 16 * 32;          // warps 0-7 epilogue, 8-11 staging/output group, 12 copy producer, 13 MMA issuer, 14-15 idle
-constexpr int TC_EPI_THREADS = 256;
+constexpr int TC_EPI_WARPS = 16;              // 4 warps per SM sub-partition: the cell update hides MUFU / TMEM latency across warps
+constexpr int TC_UPT = 32 / (TC_EPI_WARPS / 4);   // hidden units per epilogue thread per 32-unit chunk (8)
+constexpr int TC_WARP_AUX0 = TC_EPI_WARPS;    // 4 warps: window staging (encoder input) / output Linear + error (decoder)
+constexpr int TC_WARP_PROD = TC_EPI_WARPS + 4, TC_WARP_MMA = TC_EPI_WARPS + 5;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 8) * 32;   // epilogue | staging/output group | copy producer | MMA issuer | 2 idle
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_REG_EPI = 88, TC_REG_AUX = 64;       // setmaxnreg budgets: 16*32*88 + 8*32*64 = 61440 of 65536 registers
 constexpr float NLOG2E = -1.4426950408889634f;
 
 enum { IN_X = 0, IN_STREAM = 1, IN_CONST = 2 };
@@ -76,7 +79,7 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 __device__ __forceinline__ void aux_bar_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // LSTM cell from pre-scaled gate arguments (ai = -log2e*a_i, af, ao likewise, ag = -2log2e*a_g):
@@ -131,8 +134,9 @@ struct EpiCtx {
 // so the hot loop of the epilogue is ~11 KB of code instead of ~41 KB -- the fully unrolled form overflowed the 32 KB
 // L1.5 instruction cache (ncu: 25 % of the epilogue's issue slots were stall_no_inst).
 template <int H, int SINK>
-__device__ __forceinline__ void epi_chunk(const EpiCtx& x, int c, uint32_t acc_parity, float (&cst)[16]) {
+__device__ __forceinline__ void epi_chunk(const EpiCtx& x, int c, uint32_t acc_parity, float (&cst)[TC_UPT]) {
     using S = TcSmem<H>;
+    static_assert(TC_UPT == 8, "one batch of 8 units per thread per chunk");
     const int b = c & 1;
     {
         const long long tw0 = clock64();
@@ -140,43 +144,37 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& x, int c, uint32_t acc_p
         x.prof[0] += clock64() - tw0;
     }
     tc_fence_after_sync();
-    const int ub = c * 32 + x.wg * 16;                              // first hidden unit of this thread's slice
+    const int u0 = c * 32 + x.wg * 8;                                // first hidden unit of this thread's slice
+    uint32_t g0[8], g1[8], g2[8], g3[8];
+    const uint32_t abase = x.t_acc + x.lane_base + (uint32_t)(b * 128 + x.wg * 8);
+    tmem_ld8(abase + 0, g0);
+    tmem_ld8(abase + 32, g1);
+    tmem_ld8(abase + 64, g2);
+    tmem_ld8(abase + 96, g3);
+    tmem_ld_wait();
+    tc_fence_before_sync();                                          // accumulator slice in registers: release it
+    __syncwarp();
+    if (x.lane == 0) mbar_arrive(&x.bars->acc_empty[b]);
+    float hv[8];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        uint32_t g0[8], g1[8], g2[8], g3[8];
-        const uint32_t abase = x.t_acc + x.lane_base + (uint32_t)(b * 128 + x.wg * 16 + half * 8);
-        tmem_ld8(abase + 0, g0);
-        tmem_ld8(abase + 32, g1);
-        tmem_ld8(abase + 64, g2);
-        tmem_ld8(abase + 96, g3);
-        tmem_ld_wait();
-        if (half == 1) {                                             // accumulator slice fully in registers: release it
-            tc_fence_before_sync();
-            __syncwarp();
-            if (x.lane == 0) mbar_arrive(&x.bars->acc_empty[b]);
-        }
-        const int u0 = ub + half * 8;
-        float hv[8];
+    for (int u = 0; u < 8; ++u) {
+        const float4 bb = *reinterpret_cast<const float4*>(x.bias_s + (u0 + u) * 4);
+        lstm_cell(__uint_as_float(g0[u]) + bb.x, __uint_as_float(g1[u]) + bb.y, __uint_as_float(g2[u]) + bb.z,
+                  __uint_as_float(g3[u]) + bb.w, cst[u], hv[u]);
+    }
+    uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const float4 bb = *reinterpret_cast<const float4*>(x.bias_s + (u0 + u) * 4);
-            lstm_cell(__uint_as_float(g0[u]) + bb.x, __uint_as_float(g1[u]) + bb.y, __uint_as_float(g2[u]) + bb.z,
-                      __uint_as_float(g3[u]) + bb.w, cst[half * 8 + u], hv[u]);
-        }
-        uint32_t hi[4], lo[4];
+    for (int j = 0; j < 4; ++j) split_f16x2(hv[2 * j], hv[2 * j + 1], hi[j], lo[j]);
+    tmem_st4(x.hbuf + x.lane_base + (uint32_t)(u0 >> 1), hi);
+    tmem_st4(x.hbuf + x.lane_base + (uint32_t)(H / 2 + (u0 >> 1)), lo);
+    if (SINK == SINK_STREAM) {
+        const int off = ((u0 >> 3) * 16 + (x.row >> 3)) * 128 + (x.row & 7) * 16;
+        *reinterpret_cast<uint4*>(x.img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(x.img + S::IMGH + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    } else if (SINK == SINK_LAST_ENC) {
+        if (x.last_step) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split_f16x2(hv[2 * j], hv[2 * j + 1], hi[j], lo[j]);
-        tmem_st4(x.hbuf + x.lane_base + (uint32_t)(u0 >> 1), hi);
-        tmem_st4(x.hbuf + x.lane_base + (uint32_t)(H / 2 + (u0 >> 1)), lo);
-        if (SINK == SINK_STREAM) {
-            const int off = ((u0 >> 3) * 16 + (x.row >> 3)) * 128 + (x.row & 7) * 16;
-            *reinterpret_cast<uint4*>(x.img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(x.img + S::IMGH + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        } else if (SINK == SINK_LAST_ENC) {
-            if (x.last_step) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) x.hT[(u0 + u) * TCM + x.row] = hv[u];
-            }
+            for (int u = 0; u < 8; ++u) x.hT[(u0 + u) * TCM + x.row] = hv[u];
         }
     }
 }
@@ -207,11 +205,11 @@ __device__ __forceinline__ void epi_pass(const PassCtx& pc, const VaeDev& P, con
     const int T = pc.T;
     for (int i = tid; i < H * 4; i += TC_EPI_THREADS) pc.bias_s[i] = __ldg(bias_g + i);
     epi_bar_sync();
-    float cst[NCH][16];
+    float cst[NCH][TC_UPT];
 #pragma unroll
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
-        for (int u = 0; u < 16; ++u) cst[c][u] = 0.f;
+        for (int u = 0; u < TC_UPT; ++u) cst[c][u] = 0.f;
     uint32_t nacc0 = acc_cnt.n0, nacc1 = acc_cnt.n1;
     for (int t = 0; t < T; ++t) {
         const uint32_t hbuf = pc.t_h + (uint32_t)((t & 1) * H);
@@ -224,7 +222,7 @@ __device__ __forceinline__ void epi_pass(const PassCtx& pc, const VaeDev& P, con
             epi_chunk<H, SINK>(ctx, c, par, cst[0]);
             if constexpr (NCH > 1) {                           // rotate the cell state: chunk c+1's state moves to cst[0]
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
+                for (int u = 0; u < TC_UPT; ++u) {
                     const float t0 = cst[0][u];
 #pragma unroll
                     for (int k = 0; k + 1 < NCH; ++k) cst[k][u] = cst[k + 1][u];
@@ -619,8 +617,8 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
         for (int i = 0; i < TC_NST; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 1);
-            mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 8);
-            mbar_init(&bars->h_full[i], 8);
+            mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], TC_EPI_WARPS);
+            mbar_init(&bars->h_full[i], TC_EPI_WARPS);
         }
         mbar_init(&bars->xhat_full, 1); mbar_init(&bars->xhat_empty, 4);
         fence_mbar_init();
@@ -681,8 +679,8 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
     // Role groups at top level so that each group's code is dominated by its setmaxnreg: the two epilogue
     // warpgroups take 208 registers per thread (cell state + accumulator slices + deep ILP), the
     // producer / MMA / staging warpgroup drops to 88.  CTA-wide phases meet at barrier 0.
-    if (warp < 8) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    if (warp < TC_EPI_WARPS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REG_EPI));
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             pc.n0 = (long long)tile * TCM;
             pc.nvalid = (int)min((long long)TCM, n_eff - pc.n0);
@@ -704,7 +702,7 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
             }
         }
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REG_AUX));
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             pc.n0 = (long long)tile * TCM;
             pc.nvalid = (int)min((long long)TCM, n_eff - pc.n0);
