@@ -10,8 +10,9 @@
 
 namespace shm {
 
-constexpr int CP_THREADS = 256;
-constexpr int CP_ITEMS = 8;
+constexpr int CP_THREADS = 1024;
+constexpr int CP_ITEMS = 32;          // 32768 scores (128 KB) per tile: one fat CTA per SM keeps the look-back window short
+                                      // (~#SM tiles in flight) and 128 KB of loads in flight per SM
 constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
 
 constexpr unsigned long long ST_AGG = 1ull << 62;
@@ -40,26 +41,42 @@ compact_kernel(const float* __restrict__ score, float thr, long long N, unsigned
     if (tile >= n_tiles) return;
     const long long base = (long long)tile * CP_TILE + (long long)tid * CP_ITEMS;
 
-    float v[CP_ITEMS];
-    if (vec_ok && base + CP_ITEMS <= N) {
-        const float4 a = __ldcs(reinterpret_cast<const float4*>(score + base));
-        const float4 b = __ldcs(reinterpret_cast<const float4*>(score + base) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < CP_ITEMS; ++i) v[i] = (base + i < N) ? score[base + i] : -INFINITY;
-    }
+    __shared__ __align__(16) unsigned char s_nib[CP_TILE / 4];
+    const long long tile_base = (long long)tile * CP_TILE;
+    const bool full = vec_ok && tile_base + CP_TILE <= N;
     unsigned bits = 0;
+    if (full) {
+        // coalesced 16-byte loads (consecutive lanes -> consecutive float4s), flags parked as nibbles in shared memory,
+        // then every thread picks up the 32 consecutive scores it owns for the scan
+        const float4* s4 = reinterpret_cast<const float4*>(score + tile_base);
 #pragma unroll
-    for (int i = 0; i < CP_ITEMS; ++i) bits |= (v[i] > thr && base + i < N) ? (1u << i) : 0u;   // NaN > thr is false, as NumPy
+        for (int q = 0; q < CP_ITEMS / 4; ++q) {
+            const float4 a = __ldcs(s4 + q * CP_THREADS + tid);
+            s_nib[q * CP_THREADS + tid] = (unsigned char)((a.x > thr ? 1u : 0u) | (a.y > thr ? 2u : 0u) | (a.z > thr ? 4u : 0u) |
+                                                          (a.w > thr ? 8u : 0u));          // NaN > thr is false, as NumPy
+        }
+        __syncthreads();
+        const unsigned long long nb = *reinterpret_cast<const unsigned long long*>(s_nib + tid * (CP_ITEMS / 4));
+#pragma unroll
+        for (int j = 0; j < CP_ITEMS / 4; ++j) bits |= (unsigned)((nb >> (8 * j)) & 0xFull) << (4 * j);
+    } else {
+#pragma unroll 4
+        for (int i = 0; i < CP_ITEMS; ++i) bits |= (base + i < N && score[base + i] > thr) ? (1u << i) : 0u;
+    }
     const int cnt = __popc(bits);
 
     if (flag) {
-        if (vec_ok && base + CP_ITEMS <= N) {
-            unsigned long long packed = 0;
+        if (full) {
 #pragma unroll
-            for (int i = 0; i < CP_ITEMS; ++i) packed |= (unsigned long long)((bits >> i) & 1u) << (8 * i);
-            *reinterpret_cast<unsigned long long*>(flag + base) = packed;
+            for (int h = 0; h < CP_ITEMS / 16; ++h) {
+                unsigned long long p0 = 0, p1 = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    p0 |= (unsigned long long)((bits >> (16 * h + i)) & 1u) << (8 * i);
+                    p1 |= (unsigned long long)((bits >> (16 * h + 8 + i)) & 1u) << (8 * i);
+                }
+                reinterpret_cast<ulonglong2*>(flag + base)[h] = make_ulonglong2(p0, p1);
+            }
         } else {
             for (int i = 0; i < CP_ITEMS; ++i) if (base + i < N) flag[base + i] = (bits >> i) & 1u;
         }
@@ -145,7 +162,7 @@ extern "C" int shm_compact(const float* score, float thr, int64_t N, uint8_t* fl
     SHM_CUDA(cudaMemsetAsync(workspace, 0, (size_t)shm_compact_workspace_bytes(N), st));
     int* ticket = static_cast<int*>(workspace);
     unsigned long long* status = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + 16);
-    const int vec_ok = ((reinterpret_cast<uintptr_t>(score) & 15) == 0) && ((reinterpret_cast<uintptr_t>(flag) & 7) == 0);
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(score) & 15) == 0) && ((reinterpret_cast<uintptr_t>(flag) & 15) == 0);
     compact_kernel<<<n_tiles, CP_THREADS, 0, st>>>(score, thr, N, flag, idx, count, ticket, status, n_tiles, vec_ok);
     SHM_LAUNCH_CHECK();
     return SHM_OK;

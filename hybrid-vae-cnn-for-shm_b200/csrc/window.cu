@@ -49,6 +49,60 @@ window_normalize_kernel(WinSrc src, const int* __restrict__ idx, long long N, fl
     }
 }
 
+// Tile kernel for sources whose windows are whole rows apart (a series [rows, d_all] with an integer row stride, or
+// materialised windows): a CTA stages the rows its group of windows touches into shared memory ONCE -- channel select,
+// normalise, clip, NaN policy applied once per source element instead of once per output element (T/stride times fewer
+// IEEE divisions at stride 1) -- and every window then is a plain shared -> global copy (one LDS.128 + one streaming
+// STG.128 per 16 output bytes, one warp per window, no index divisions).  Same arithmetic (win_transform), hence the
+// same bits, as the generic kernel.
+constexpr int WT_THREADS = 256;
+constexpr int WT_SMEM_FLOATS = 11 * 1024;          // 44 KB tile (static shared memory)
+
+__global__ void __launch_bounds__(WT_THREADS)
+window_tile_kernel(WinSrc src, const int* __restrict__ idx, long long N, float* __restrict__ out, int group, int step_rows) {
+    __shared__ __align__(16) float tile[WT_SMEM_FLOATS];
+    __shared__ int s_chan[SHM_MAX_D];
+    const int T = src.T, D = src.D, TD = T * D;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < D) s_chan[tid] = src.chan[tid];
+    const long long groups = (N + group - 1) / group;
+    const int slab = (idx == nullptr) ? step_rows * D : TD;         // floats between consecutive windows in the tile
+    const bool vec = (slab % 4 == 0) && (TD % 4 == 0);
+    for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
+        const long long n0 = g * group;
+        const int nw = (int)min((long long)group, N - n0);
+        __syncthreads();
+        if (idx == nullptr) {
+            // rows [n0*step, n0*step + (nw-1)*step + T) of the source, shared by the windows of the group
+            const int rows = (nw - 1) * step_rows + T;
+            const float* base = src.base + n0 * src.win_stride;
+            for (int i = tid; i < rows * D; i += WT_THREADS) {
+                const int r = i / D, d = i - r * D;
+                tile[i] = win_transform(src, __ldg(base + (long long)r * src.row_stride + s_chan[d]), d);
+            }
+        } else {
+            for (int i = tid; i < nw * TD; i += WT_THREADS) {       // gathered windows: one private slab per window
+                const int w = i / TD, e = i - w * TD;
+                const int r = e / D, d = e - r * D;
+                const float* base = src.base + (long long)idx[n0 + w] * src.win_stride;
+                tile[i] = win_transform(src, __ldg(base + (long long)r * src.row_stride + s_chan[d]), d);
+            }
+        }
+        __syncthreads();
+        if (vec) {
+            const int c4 = TD >> 2;
+            for (int w = warp; w < nw; w += WT_THREADS / 32) {
+                const float4* s4 = reinterpret_cast<const float4*>(tile + w * slab);
+                float4* o4 = reinterpret_cast<float4*>(out + (n0 + w) * TD);
+                for (int c = lane; c < c4; c += 32) __stcs(o4 + c, s4[c]);
+            }
+        } else {
+            for (int w = warp; w < nw; w += WT_THREADS / 32)
+                for (int e = lane; e < TD; e += 32) __stcs(out + (n0 + w) * TD + e, tile[w * slab + e]);
+        }
+    }
+}
+
 }  // namespace shm
 
 extern "C" int shm_window_normalize(const shm_window_src* src_host, const int32_t* idx, int64_t N, float* out,
@@ -62,11 +116,32 @@ extern "C" int shm_window_normalize(const shm_window_src* src_host, const int32_
     int dev = 0;
     SHM_CUDA(cudaGetDevice(&dev));
     if ((rc = check_device(dev)) != SHM_OK) return rc;
-    const long long groups = (N + WIN_PER_CTA - 1) / WIN_PER_CTA;
     const int sms = device_sm_count(dev);
-    const int grid = (int)min(groups, (long long)sms * 8 * 4);     // multiple of the SM count, 8 CTAs/SM resident
-    const bool vec4 = ((w.T * w.D) % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool out16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    // tile path: windows a whole number of rows apart (series or materialised windows) whose T*D slab fits the tile
+    const int TD = w.T * w.D;
+    if (out16 && TD <= WT_SMEM_FLOATS && w.row_stride > 0 && w.win_stride > 0 && w.win_stride % w.row_stride == 0 &&
+        w.win_stride / w.row_stride < (1 << 20)) {
+        const int step_rows = (int)(w.win_stride / w.row_stride);
+        int group;
+        if (idx == nullptr) {                                       // consecutive windows share the staged rows
+            const int max_rows = WT_SMEM_FLOATS / w.D;
+            group = (max_rows - w.T) / step_rows + 1;
+            group = group > 64 ? 64 : group;
+        } else {                                                    // gathered windows: one slab each
+            group = WT_SMEM_FLOATS / TD;
+            group = group > 16 ? 16 : group;
+        }
+        const long long tgroups = (N + group - 1) / group;
+        const int tgrid = (int)min(tgroups, (long long)sms * 16);
+        window_tile_kernel<<<tgrid, WT_THREADS, 0, st>>>(w, idx, N, out, group, step_rows);
+        SHM_LAUNCH_CHECK();
+        return SHM_OK;
+    }
+    const long long groups = (N + WIN_PER_CTA - 1) / WIN_PER_CTA;
+    const int grid = (int)min(groups, (long long)sms * 8 * 4);     // multiple of the SM count, 8 CTAs/SM resident
+    const bool vec4 = ((w.T * w.D) % 4 == 0) && out16;
     if (vec4) window_normalize_kernel<true><<<grid, WIN_THREADS, 0, st>>>(w, idx, N, out);
     else window_normalize_kernel<false><<<grid, WIN_THREADS, 0, st>>>(w, idx, N, out);
     SHM_LAUNCH_CHECK();
