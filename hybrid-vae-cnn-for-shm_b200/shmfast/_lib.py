@@ -49,6 +49,13 @@ class Cnn4dofWeights(C.Structure):
                 ("bn_var", _vp * 2), ("fc1_w", _vp), ("fc1_b", _vp), ("fc2_w", _vp), ("fc2_b", _vp), ("bn_eps", C.c_float)]
 
 
+class ExtractCfg(C.Structure):
+    _fields_ = [("T", C.c_int32), ("stride", C.c_int32), ("ma_window", C.c_int32), ("struct_channel_mask", C.c_int32),
+                ("obstruction_sentinel", C.c_double), ("raw_diff_th", C.c_double), ("raw_abs_th", C.c_double),
+                ("clean_max_jump", C.c_double), ("clean_max_abs", C.c_double), ("raw_invalid_ratio_fault", C.c_float),
+                ("flat_var_eps", C.c_float), ("force_range_for_flatline", C.c_float), ("allow_max", C.c_float)]
+
+
 class CnnOlWeights(C.Structure):
     _fields_ = [("conv_w", _vp * 4), ("conv_b", _vp * 4), ("gn_w", _vp * 4), ("gn_b", _vp * 4), ("fc1_w", _vp),
                 ("fc1_b", _vp), ("fc2_w", _vp), ("fc2_b", _vp), ("gn_eps", C.c_float)]
@@ -88,6 +95,8 @@ SIGNATURES = {
     "shm_cnnol_forward": (C.c_int, [_vp, C.POINTER(WindowSrc), _vp, _vp, C.c_int64, _vp, _vp, _vp]),
     "shm_cnnol_set_engine": (C.c_int, [_vp, C.c_int]),
     "shm_cnnol_engine": (C.c_int, [_vp]),
+    "shm_openlab_extract_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "shm_openlab_extract": (C.c_int, [_vp, C.c_int64, C.POINTER(ExtractCfg)] + [_vp] * 15),
     "shm_stitch_segment_rmse": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _vp, _vp, _vp,
                                           C.c_int32, _vp, _vp, _vp]),
     "shm_percentile_workspace_bytes": (C.c_int64, [C.c_int64]),

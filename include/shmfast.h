@@ -272,6 +272,37 @@ int shm_cnnol_set_engine(shm_cnnol* h, int engine);
 int shm_cnnol_engine(const shm_cnnol* h);
 
 /* ---------------------------------------------------------------------------------------------
+ * openLAB extraction front-end: what feeds the hybrid path.  One run's parsed catman
+ * columns raw [R,4] float32 = DMS_1, LWA_2, LWA_3, LWA_4 (as _to_float yields them,
+ * 20250506_openLAB_tests/Codes/01_extract_windows_and_labels.py:58-59) -> obstruction sentinel -> NaN (:117-119),
+ * provider AND-rule outlier masks (:65-83), clean_openlab_and_rule (feature_utils.py:49-99: AND-rule removal, linear
+ * interpolation, moving average; fp64 -> fp32), rows with a finite DMS kept (:151-156), and per window of
+ * (T, stride) (:159-214): mask ratios, structural envelope u_min/u_max over the selected clean channels, DMS range,
+ * load-aware flatline flag and the label (0 Normal, 1 Sensor Fault, 2 Structural Fault; SF > ST > Normal).
+ * a_clean / a_raw [R,4]: the first *rows_kept rows are valid; window w is rows [w*stride, w*stride+T) of them -- describe
+ * them to shm_vae_score / shm_cnnol_forward with a shm_window_src (win_stride = stride*4, row_stride = 4).
+ * Per-window outputs hold (R-T)/stride+1 entries, the first *n_windows valid.  Bit-identical to the reference.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t T, stride;                    /* config.py:27-28  SEQ_LEN 200, STRIDE 20 */
+    int32_t ma_window;                    /* config.py:45     MOVING_AVG_WINDOW 5 (odd, or <= 1 for none) */
+    int32_t struct_channel_mask;          /* bit k = LWA_{2+k} defines the structural envelope; 01:50 uses LWA_3 only = 2 */
+    double obstruction_sentinel;          /* config.py:42     -1e5 */
+    double raw_diff_th, raw_abs_th;       /* config.py:50-51  1.0, 65.0 (>=, float32 arithmetic) */
+    double clean_max_jump, clean_max_abs; /* config.py:43-44  1.0, 65.0 (>, float64 arithmetic) */
+    float raw_invalid_ratio_fault;        /* config.py:52     0.05 */
+    float flat_var_eps;                   /* config.py:55     1e-6 */
+    float force_range_for_flatline;       /* config.py:56     5.0 */
+    float allow_max;                      /* config.py:37     20.0 */
+} shm_openlab_extract_cfg;
+
+int64_t shm_openlab_extract_workspace_bytes(int64_t R);
+int shm_openlab_extract(const float* raw, int64_t R, const shm_openlab_extract_cfg* cfg_host, float* a_clean, float* a_raw,
+                        int32_t* rows_kept, int32_t* n_windows, int32_t* label, float* u_min, float* u_max, float* dms_range,
+                        float* raw_invalid_ratio, float* raw_outlier_ratio, float* removed_ratio, int32_t* flatline_loadaware,
+                        int32_t* all_nan_struct, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * 1_DOF post-processing: overlap-average reconstructed windows back to a series, de-standardise,
  * RMSE per `segment_len` rows over all channels -- stitch_windows / destandardize / segment_rmse
  * (1_DOF/Scripts/datasets.py:21-22,38-71; call site 04_test_seen_variants.py:296-311).  fp64 like

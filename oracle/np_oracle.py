@@ -434,3 +434,110 @@ def adam_clip_step(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, wd=1e-
     denom = (np.sqrt(v) / f(bc2s) + f(eps)).astype(f)
     p = (p - f(lr / bc1) * (m / denom)).astype(f)
     return p, m, v, float(total)
+
+
+# --------------------------------------------------------------------------------------
+# f2  openLAB extraction front-end: cleaned/raw series -> windows -> rule labels
+#     (20250506_openLAB_tests/Codes/01_extract_windows_and_labels.py:86-236, feature_utils.py:49-99,130-177)
+# --------------------------------------------------------------------------------------
+OPENLAB_EXTRACT_CFG = dict(T=200, stride=20, sentinel=-1e5, raw_diff_th=1.0, raw_abs_th=65.0, clean_max_jump=1.0,
+                           clean_max_abs=65.0, ma_window=5, raw_invalid_ratio_fault=0.05, flat_var_eps=1e-6,
+                           force_range_for_flatline=5.0, allow_max=20.0, struct_channels=(2,))   # config.py:27-56; 01:50 (LWA_3)
+LABEL_NORMAL, LABEL_SENSOR_FAULT, LABEL_STRUCT_FAULT = 0, 1, 2
+
+
+def provider_outlier_mask(u: np.ndarray, diff_th: float, abs_th: float) -> np.ndarray:
+    """provider_raw_outlier_mask_AND, 01_extract_windows_and_labels.py:65-83 (float32 arithmetic)."""
+    u = np.asarray(u, dtype=np.float32)
+    m = ~np.isfinite(u)
+    if u.size > 1:
+        with np.errstate(invalid="ignore"):
+            du = np.abs(np.diff(u))
+            m[1:] |= (du >= np.float32(diff_th)) & (np.abs(u[1:]) >= np.float32(abs_th))
+    return m.astype(np.float32)
+
+
+def clean_and_rule(x: np.ndarray, max_jump: float, max_abs: float, ma_window: int):
+    """clean_openlab_and_rule, feature_utils.py:49-99, restated without the Python loop.  The loop marks sample i removed
+    when x2[i-1] is already NaN, so the FIRST invalid sample or AND-rule hit removes everything after it; pandas'
+    interpolate(limit_direction="both") then holds the last valid value to the end (all-NaN if nothing is valid), and
+    np.convolve(mode="same") with a flat kernel is a centred, zero-padded moving average.  fp64 -> float32."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.size
+    trig = ~np.isfinite(x)
+    if n > 1:
+        with np.errstate(invalid="ignore"):
+            trig[1:] |= (np.abs(x[1:] - x[:-1]) > float(max_jump)) & (np.abs(x[1:]) > float(max_abs))
+    hits = np.flatnonzero(trig)
+    i0 = int(hits[0]) if hits.size else n
+    removed = np.zeros(n, dtype=bool)
+    removed[i0:] = True
+    xi = x.copy()
+    xi[i0:] = x[i0 - 1] if i0 > 0 else np.nan
+    if ma_window and ma_window > 1:
+        w = int(ma_window)
+        half_l, half_r = w // 2, (w - 1) // 2           # np.convolve 'same': output i sums x[i-half_r .. i+half_l] for odd w both = w//2
+        pad = np.concatenate([np.zeros(half_l), xi, np.zeros(half_l)])
+        k = 1.0 / float(w)
+        acc = np.zeros(n, dtype=np.float64)
+        for j in range(w):                              # ascending sample index, multiply then add (cblas_ddot scalar tail)
+            acc = acc + pad[j:j + n] * k
+        xi = acc
+        del half_r
+    return xi.astype(np.float32), removed.astype(np.float32)
+
+
+def openlab_extract_run(raw: np.ndarray, cfg: dict = OPENLAB_EXTRACT_CFG) -> dict:
+    """One run of 01_extract_windows_and_labels.py:104-236.  raw [R,4] float32 = DMS_1, LWA_2, LWA_3, LWA_4 as parsed by
+    _to_float (:58-59).  Returns the kept series A_clean/A_raw [Rk,4] float32 (windows are views: start i*stride, length T),
+    per-window metadata and integer labels (0 Normal, 1 Sensor Fault, 2 Structural Fault)."""
+    raw = np.asarray(raw, dtype=np.float32)
+    T, S = int(cfg["T"]), int(cfg["stride"])
+    dms = raw[:, 0].copy()
+    u = [raw[:, c].copy() for c in (1, 2, 3)]
+    for a in u:
+        with np.errstate(invalid="ignore"):
+            a[a <= np.float32(cfg["sentinel"])] = np.nan                                  # :117-119
+    out = [provider_outlier_mask(a, cfg["raw_diff_th"], cfg["raw_abs_th"]) for a in u]     # :122-124
+    inv = [(~np.isfinite(a)).astype(np.float32) for a in u]
+    raw_out = np.maximum.reduce(out).astype(np.float32)
+    raw_inv = np.maximum.reduce(inv).astype(np.float32)
+    cl = [clean_and_rule(a, cfg["clean_max_jump"], cfg["clean_max_abs"], cfg["ma_window"]) for a in u]   # :134-142
+    removed = np.maximum.reduce([c[1] for c in cl]).astype(np.float32)
+    A_clean = np.stack([dms, cl[0][0], cl[1][0], cl[2][0]], axis=1).astype(np.float32)
+    A_raw = np.stack([dms, u[0], u[1], u[2]], axis=1).astype(np.float32)
+    keep = np.isfinite(dms)                                                                # :151-156
+    A_clean, A_raw, raw_out, raw_inv, removed = A_clean[keep], A_raw[keep], raw_out[keep], raw_inv[keep], removed[keep]
+    n = A_clean.shape[0]
+    nW = 0 if n < T else (n - T) // S + 1
+    starts = np.arange(nW, dtype=np.int64) * S
+    res = dict(A_clean=A_clean, A_raw=A_raw, rows_kept=n, n_windows=nW, win_start_idx=starts)
+    if nW == 0:
+        return res
+    win = lambda a: np.stack([a[i:i + T] for i in starts]).astype(np.float32)
+    Xc = win(A_clean)
+    f32 = np.float32
+    raw_out_ratio = win(raw_out).mean(axis=1).astype(f32)                                  # :170-176
+    raw_inv_ratio = win(raw_inv).mean(axis=1).astype(f32)
+    removed_ratio = win(removed).mean(axis=1).astype(f32)
+    U = np.stack([Xc[:, :, j + 1 - 1] for j in cfg["struct_channels"]], axis=2)          # :181 (indices into Xc: 1..3)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        u_min = np.nanmin(U, axis=(1, 2)).astype(f32)
+        u_max = np.nanmax(U, axis=(1, 2)).astype(f32)
+        all_nan = (~np.isfinite(u_min)) | (~np.isfinite(u_max))
+        dms_win = Xc[:, :, 0]
+        dms_rng = (np.nanmax(dms_win, axis=1) - np.nanmin(dms_win, axis=1)).astype(f32)
+        u_var = np.nanvar(U, axis=(1, 2)).astype(f32)
+    flat = ((u_var < cfg["flat_var_eps"]) & (dms_rng > cfg["force_range_for_flatline"])).astype(np.int32)   # :193
+    sensor = ((raw_inv_ratio >= float(cfg["raw_invalid_ratio_fault"])) | (raw_out_ratio > 0.0) | (removed_ratio > 0.0) |
+              (flat == 1) | all_nan)                                                       # :200-206
+    struct = u_max > float(cfg["allow_max"])                                               # :209
+    label = np.full(nW, LABEL_NORMAL, dtype=np.int32)
+    label[struct & ~sensor] = LABEL_STRUCT_FAULT
+    label[sensor] = LABEL_SENSOR_FAULT                                                     # :212-214
+    res.update(label=label, u_min=u_min, u_max=u_max, dms_range=dms_rng, raw_invalid_ratio=raw_inv_ratio,
+               raw_outlier_ratio=raw_out_ratio, removed_ratio=removed_ratio, flatline_loadaware=flat,
+               all_nan_struct=all_nan.astype(np.int32), u_var=u_var)
+    return res

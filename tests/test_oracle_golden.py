@@ -196,3 +196,59 @@ def test_train_step_port_matches_reference(golden_dir, name):
         assert np.mean(np.abs(got_p - ref_p) <= 1e-6) > 0.97, n
         o += k
     assert o == fg.size
+
+
+def _frontend_runs(g):
+    offs, wpr = g["run_row_offsets"], g["win_per_run"]
+    w0 = 0
+    for r in range(len(wpr)):
+        yield g["raw"][offs[r]:offs[r + 1]], w0, w0 + int(wpr[r])
+        w0 += int(wpr[r])
+
+
+FRONTEND_F32 = ("u_min", "u_max", "dms_range", "raw_invalid_ratio", "raw_outlier_ratio", "removed_ratio")
+FRONTEND_I32 = ("flatline_loadaware", "all_nan_struct")
+
+
+def test_openlab_frontend_oracle_bit_exact(golden_dir):
+    """np_oracle.openlab_extract_run against the reference's own 01_extract_windows_and_labels.py outputs on the reference's
+    raw data (7 runs, 6,432 windows): labels, every window_labels.csv column and the windows themselves, bit for bit."""
+    g = np.load(golden_dir / "openlab_frontend.npz")
+    sample = {int(i): k for k, i in enumerate(g["sample_idx"])}
+    total = 0
+    for raw, w0, w1 in _frontend_runs(g):
+        r = O.openlab_extract_run(raw)
+        assert r["n_windows"] == w1 - w0
+        assert np.array_equal(r["win_start_idx"], g["win_start_idx"][w0:w1])
+        assert np.array_equal(r["label"], g["label"][w0:w1])
+        for k in FRONTEND_F32:
+            assert np.array_equal(r[k], g[k][w0:w1], equal_nan=True), k
+        for k in FRONTEND_I32:
+            assert np.array_equal(r[k], g[k][w0:w1]), k
+        Xc = np.stack([r["A_clean"][i:i + 200] for i in r["win_start_idx"]])
+        Xr = np.stack([r["A_raw"][i:i + 200] for i in r["win_start_idx"]])
+        assert np.array_equal(np.nansum(Xc.astype(np.float64), axis=(1, 2)), g["xc_sum"][w0:w1])
+        assert np.array_equal(np.nansum(Xr.astype(np.float64), axis=(1, 2)), g["xr_sum"][w0:w1])
+        assert np.array_equal(np.isnan(Xr).sum(axis=(1, 2)), g["xr_nan"][w0:w1])
+        for w in range(w0, w1):
+            if w in sample:
+                assert np.array_equal(Xc[w - w0], g["xc_sample"][sample[w]], equal_nan=True)
+                assert np.array_equal(Xr[w - w0], g["xr_sample"][sample[w]], equal_nan=True)
+        total += w1 - w0
+    assert total == 6432 and np.bincount(g["label"]).tolist() == [1865, 3423, 1144]
+
+
+def test_openlab_frontend_edge_cases():
+    """Semantics the real data does not exercise: non-finite DMS rows dropped, a run shorter than one window, an all-invalid
+    channel, no trigger at all (cleaning = plain moving average)."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    raw = (10 + rng.standard_normal((900, 4))).astype(np.float32)
+    raw[100:105, 0] = np.nan                       # DMS gaps -> rows removed before windowing
+    raw[:, 3] = -2e5                               # LWA_4 obstructed throughout -> all NaN after the sentinel
+    r = O.openlab_extract_run(raw)
+    assert r["rows_kept"] == 895 and r["n_windows"] == (895 - 200) // 20 + 1
+    assert np.all(r["label"] == 1) and np.all(r["raw_invalid_ratio"] == 1.0)
+    assert np.isnan(r["A_clean"][:, 3]).all()
+    xi, rem = O.clean_and_rule(raw[:, 1], 1.0, 65.0, 5)
+    assert rem.sum() == 0 and np.allclose(xi[2:-2], np.convolve(raw[:, 1].astype(np.float64), np.ones(5) / 5, "same")[2:-2].astype(np.float32))
+    assert O.openlab_extract_run(raw[:150])["n_windows"] == 0
