@@ -43,8 +43,9 @@ template <int L> struct OlDer {
     static constexpr int R = HH * G::RPH;                  // staged rows
     static constexpr int NPAIR = (G::HIN + PH - 1) / PH;
     static constexpr int NCC = G::CIN / 16;
-    static constexpr int A_IMG = R * 32;                   // bytes: R rows x 16 fp16
-    static constexpr int A_STAGE = 6 * A_IMG;              // 3 df shifts x {hi, lo}
+    static constexpr int A_IMG = R * 32;                   // bytes: R rows x 16 fp16 (2 k-core blocks of R x 16 B: row r at r*16)
+    static constexpr int A_STAGE = 6 * A_IMG;              // shared memory: 3 df shifts x {hi, lo}
+    static constexpr int A_GSTAGE = 2 * A_IMG;             // global memory: the unshifted image only, {hi, lo}
     static constexpr int TG = (G::NOUT <= 64) ? 3 : 1;     // taps per weight stage (small-N MMAs are short: fewer barrier round trips)
     static constexpr int B_TAP = G::NOUT * 64;             // {hi, lo} x [NOUT x 16] fp16 of one tap
     static constexpr int B_STAGE = TG * B_TAP;
@@ -60,6 +61,13 @@ template <int L> struct OlDer {
 };
 
 __device__ __forceinline__ float silu_acc(float x) { return x / (1.0f + expf(-x)); }
+// ex2.approx (2 ulp) + rcp.approx (1 ulp): ~3e-7 relative, 4x fewer instructions; used where SiLU is the whole kernel
+__device__ __forceinline__ float silu_fast(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(-1.4426950408889634f * x, 80.f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
 
 __device__ __forceinline__ long long eff_windows(long long n_total, const int* n_dev, long long base, long long n_chunk) {
     long long e = n_total;
@@ -76,73 +84,64 @@ __global__ void __launch_bounds__(256) ol_conv1_kernel(const float* __restrict__
                                                        const int* __restrict__ idx, const int* __restrict__ n_dev, long long n_total,
                                                        long long base, long long n_chunk, float* __restrict__ out,
                                                        double* __restrict__ stats) {
-    __shared__ float xin[(OLT_T + 6) * 6];        // zero-padded plane: rows -3..202, cols -1..4
-    __shared__ __align__(16) float wk[21 * 32];   // [tap][co]
+    // thread item = (time step h, block of 4 output channels = one GroupNorm group) for all 4 sensor columns: 16 accumulators,
+    // per dt one padded input row (6 floats) and 3 float4 weight vectors feed 48 FMAs
+    __shared__ __align__(16) float xin[(OLT_T + 6) * 8];    // zero-padded plane: rows -3..202, cols -1..4 (+2 pad)
+    __shared__ __align__(16) float wk[21 * 32];             // [tap][co]
     __shared__ float bs[32];
-    __shared__ double red[8][16];
-    const int tid = threadIdx.x;
+    __shared__ float red[8][16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cb = tid & 7;                                 // channel block / GroupNorm group
     const long long n_eff = eff_windows(n_total, n_dev, base, n_chunk);
     for (int i = tid; i < 21 * 32; i += 256) { const int co = i & 31, tap = i >> 5; wk[i] = __ldg(w1 + co * 21 + tap); }
     if (tid < 32) bs[tid] = __ldg(b1 + tid);
     for (long long w = blockIdx.x; w < n_eff; w += gridDim.x) {
         const long long win = idx ? (long long)idx[base + w] : (base + w);
         __syncthreads();
-        for (int i = tid; i < (OLT_T + 6) * 6; i += 256) {
-            const int r = i / 6 - 3, c = i % 6 - 1;
+        for (int i = tid; i < (OLT_T + 6) * 8; i += 256) {
+            const int r = (i >> 3) - 3, c = (i & 7) - 1;
             xin[i] = (r >= 0 && r < OLT_T && c >= 0 && c < OLT_F) ? win_fetch(src, win, r, c) : 0.f;
         }
         __syncthreads();
-        float fs[8], fq[8];                        // per-thread partials over <= 4 positions x 4 channels: fp32 is exact enough
+        float gs = 0.f, gq = 0.f;
+        const float4 bias4 = *reinterpret_cast<const float4*>(bs + cb * 4);
+        for (int h = tid >> 3; h < OLT_T; h += 32) {
+            float acc[4][4];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) { fs[g] = 0.f; fq[g] = 0.f; }
-        for (int pos = tid; pos < OLT_T * OLT_F; pos += 256) {
-            const int h = pos >> 2, wc = pos & 3;
-            float4* o = reinterpret_cast<float4*>(out + ((size_t)w * OLT_T * OLT_F + pos) * 32);
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                float acc[16];
+            for (int q = 0; q < 4; ++q) { acc[q][0] = bias4.x; acc[q][1] = bias4.y; acc[q][2] = bias4.z; acc[q][3] = bias4.w; }
 #pragma unroll
-                for (int co = 0; co < 16; ++co) acc[co] = bs[half * 16 + co];
-#pragma unroll 1
-                for (int dt = 0; dt < 7; ++dt) {               // rolled on purpose: unrolled, ptxas hoists all 672 weights into registers
+            for (int dt = 0; dt < 7; ++dt) {
+                const float4 xa = *reinterpret_cast<const float4*>(xin + (h + dt) * 8);
+                const float2 xb = *reinterpret_cast<const float2*>(xin + (h + dt) * 8 + 4);
+                const float xr[6] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y};
 #pragma unroll
-                    for (int df = 0; df < 3; ++df) {
-                        const float x = xin[(h + dt) * 6 + wc + df];
-                        const float4* wr = reinterpret_cast<const float4*>(wk + (dt * 3 + df) * 32 + half * 16);
+                for (int df = 0; df < 3; ++df) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wk + (dt * 3 + df) * 32 + cb * 4);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 w4 = wr[q];
-                            acc[4 * q] = fmaf(x, w4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(x, w4.y, acc[4 * q + 1]);
-                            acc[4 * q + 2] = fmaf(x, w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(x, w4.w, acc[4 * q + 3]);
-                        }
+                    for (int q = 0; q < 4; ++q) {
+                        const float x = xr[q + df];
+                        acc[q][0] = fmaf(x, w4.x, acc[q][0]); acc[q][1] = fmaf(x, w4.y, acc[q][1]);
+                        acc[q][2] = fmaf(x, w4.z, acc[q][2]); acc[q][3] = fmaf(x, w4.w, acc[q][3]);
                     }
                 }
+            }
+            float* o = out + ((size_t)w * OLT_T * OLT_F + (size_t)h * OLT_F) * 32 + cb * 4;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    o[half * 4 + q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-                    fs[half * 4 + q] += (acc[4 * q] + acc[4 * q + 1]) + (acc[4 * q + 2] + acc[4 * q + 3]);
-                    fq[half * 4 + q] += fmaf(acc[4 * q], acc[4 * q], fmaf(acc[4 * q + 1], acc[4 * q + 1],
-                                        fmaf(acc[4 * q + 2], acc[4 * q + 2], acc[4 * q + 3] * acc[4 * q + 3])));
-                }
+            for (int q = 0; q < 4; ++q) {
+                *reinterpret_cast<float4*>(o + q * 32) = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+                gs += (acc[q][0] + acc[q][1]) + (acc[q][2] + acc[q][3]);
+                gq += fmaf(acc[q][0], acc[q][0], fmaf(acc[q][1], acc[q][1], fmaf(acc[q][2], acc[q][2], acc[q][3] * acc[q][3])));
             }
         }
-        double gs[8], gq[8];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) { gs[g] = (double)fs[g]; gq[g] = (double)fq[g]; }
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o); gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], o); }
-        }
-        if ((tid & 31) == 0) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) { red[tid >> 5][2 * g] = gs[g]; red[tid >> 5][2 * g + 1] = gq[g]; }
-        }
+        // lanes with the same channel block (lane & 7) reduce, then the 8 warps through shared memory (fixed order)
+        gs += __shfl_xor_sync(0xffffffffu, gs, 8); gq += __shfl_xor_sync(0xffffffffu, gq, 8);
+        gs += __shfl_xor_sync(0xffffffffu, gs, 16); gq += __shfl_xor_sync(0xffffffffu, gq, 16);
+        if (lane < 8) { red[warp][2 * lane] = gs; red[warp][2 * lane + 1] = gq; }
         __syncthreads();
         if (tid < 16) {
-            double s = 0.0;
-            for (int i = 0; i < 8; ++i) s += red[i][tid];
-            stats[(size_t)w * 16 + tid] = s;
+            double t = 0.0;
+            for (int i = 0; i < 8; ++i) t += (double)red[i][tid];
+            stats[(size_t)w * 16 + tid] = t;
         }
     }
 }
@@ -213,27 +212,12 @@ __global__ void __launch_bounds__(256) ol_act_stage_kernel(const float* __restri
 #pragma unroll
             for (int q = 0; q < 4; ++q) split_f16x2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
         }
-        unsigned char* img = staged + (((size_t)g * D::NPAIR + p) * D::NCC + cc) * D::A_STAGE + (size_t)c8 * (D::R * 16);
-        const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        const int rbase = hh * G::RPH + wi * 4;
-#pragma unroll
-        for (int df = 0; df < 3; ++df) {
-            // image df holds in[h][w + df - 1]: this source column lands at w = ws - df + 1
-            const int wd = ws - df + 1;
-            if (wd >= 0 && wd < 4) {
-                const int row = rbase + wd;
-                const size_t off = (size_t)(row >> 3) * 128 + (row & 7) * 16;
-                *reinterpret_cast<uint4*>(img + (size_t)(df * 2 + 0) * D::A_IMG + off) = vh;
-                *reinterpret_cast<uint4*>(img + (size_t)(df * 2 + 1) * D::A_IMG + off) = vl;
-            }
-        }
-        if (ws == 0 || ws == 3) {           // zero fill of the shifted copies' out-of-range column
-            const int df = ws == 0 ? 0 : 2, row = rbase + (ws == 0 ? 0 : 3);
-            const size_t off = (size_t)(row >> 3) * 128 + (row & 7) * 16;
-            *reinterpret_cast<uint4*>(img + (size_t)(df * 2 + 0) * D::A_IMG + off) = z;
-            *reinterpret_cast<uint4*>(img + (size_t)(df * 2 + 1) * D::A_IMG + off) = z;
-        }
+        // only the unshifted image goes to global memory: in the K-major core-matrix layout row r of a k-core block sits at
+        // r*16 bytes, so the GEMM's producer realises the df = -1/+1 copies as the same bytes landed 16 B later / earlier
+        unsigned char* img = staged + (((size_t)g * D::NPAIR + p) * D::NCC + cc) * D::A_GSTAGE + (size_t)c8 * (D::R * 16);
+        const int row = hh * G::RPH + wi * 4 + ws;
+        *reinterpret_cast<uint4*>(img + (size_t)row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(img + D::A_IMG + (size_t)row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -252,11 +236,11 @@ struct OlGemmArgs {
 };
 
 template <int L> struct OlBars {
-    uint64_t a_full[2], a_empty[2], b_full[OlDer<L>::NB], b_empty[OlDer<L>::NB], acc_full[2], acc_empty[2];
+    uint64_t a_landed[2], a_full[2], a_empty[2], b_full[OlDer<L>::NB], b_empty[OlDer<L>::NB], acc_full[2], acc_empty[2];
 };
 
 template <int L>
-__global__ void __launch_bounds__(224, 1) ol_conv_gemm_kernel(const OlGemmArgs a) {
+__global__ void __launch_bounds__(256, 1) ol_conv_gemm_kernel(const OlGemmArgs a) {
     using G = OlGeo<L>;
     using D = OlDer<L>;
     constexpr int NOUT = G::NOUT, KT = G::KT, RPH = G::RPH, HIN = G::HIN;
@@ -274,12 +258,12 @@ __global__ void __launch_bounds__(224, 1) ol_conv_gemm_kernel(const OlGemmArgs a
     const long long items = groups * D::NPAIR;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->a_landed[i], 1); mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
         for (int i = 0; i < D::NB; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
         fence_mbar_init();
     }
-    for (int i = tid; i < NOUT; i += 224) bias_s[i] = __ldg(a.bias + i);
+    for (int i = tid; i < NOUT; i += 256) bias_s[i] = __ldg(a.bias + i);
     if (warp == 6) tmem_alloc(tmem_holder, D::TCOLS);
     tc_fence_before_sync();
     __syncthreads();
@@ -290,16 +274,46 @@ __global__ void __launch_bounds__(224, 1) ol_conv_gemm_kernel(const OlGemmArgs a
         if (lane == 0) {
             uint32_t it = 0;
             for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-                const unsigned char* src = a.staged + (size_t)item * D::NCC * D::A_STAGE;
+                const unsigned char* src = a.staged + (size_t)item * D::NCC * D::A_GSTAGE;
+                constexpr uint32_t KB = D::R * 16;                         // one k-core block: R rows x 16 B
                 for (int cc = 0; cc < D::NCC; ++cc, ++it) {
                     const uint32_t s = it & 1;
                     mbar_wait(&bars->a_empty[s], ((it >> 1) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&bars->a_full[s], (uint32_t)D::A_STAGE);
+                    mbar_arrive_expect_tx(&bars->a_landed[s], 4u * (KB + 2u * (KB - 16u)));
+                    const unsigned char* gimg = src + (size_t)cc * D::A_GSTAGE;
+                    unsigned char* sbase = As + s * D::A_STAGE;
 #pragma unroll
-                    for (int q = 0; q < 6; ++q)
-                        bulk_g2s(As + s * D::A_STAGE + q * D::A_IMG, src + (size_t)cc * D::A_STAGE + (size_t)q * D::A_IMG,
-                                 (uint32_t)D::A_IMG, &bars->a_full[s]);
+                    for (int half = 0; half < 2; ++half)
+#pragma unroll
+                        for (int kc = 0; kc < 2; ++kc) {
+                            const unsigned char* g0 = gimg + half * D::A_IMG + kc * KB;
+                            // df = 0 holds in[w-1]: row r <- row r-1 (row 0 / every w = 0 row is zeroed by the fix-up warp)
+                            bulk_g2s(sbase + (0 * 2 + half) * D::A_IMG + kc * KB + 16, g0, KB - 16, &bars->a_landed[s]);
+                            bulk_g2s(sbase + (1 * 2 + half) * D::A_IMG + kc * KB, g0, KB, &bars->a_landed[s]);
+                            // df = 2 holds in[w+1]: row r <- row r+1 (every w = 3 row zeroed by the fix-up warp)
+                            bulk_g2s(sbase + (2 * 2 + half) * D::A_IMG + kc * KB, g0 + 16, KB - 16, &bars->a_landed[s]);
+                        }
                 }
+            }
+        }
+    } else if (warp == 7) {                            // ---- fix-up: zero fill of the shifted copies' out-of-range column
+        uint32_t it = 0;
+        constexpr uint32_t KB = D::R * 16;
+        for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+            for (int cc = 0; cc < D::NCC; ++cc, ++it) {
+                const uint32_t s = it & 1;
+                mbar_wait(&bars->a_landed[s], (it >> 1) & 1);
+                unsigned char* sbase = As + s * D::A_STAGE;
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                for (int i = lane; i < (D::R / 4) * 4; i += 32) {            // (row group of 4) x (half, k-core)
+                    const int r4 = i >> 2, hk = i & 3;
+                    const uint32_t off = (uint32_t)(hk >> 1) * D::A_IMG + (uint32_t)(hk & 1) * KB;
+                    *reinterpret_cast<uint4*>(sbase + 0 * D::A_IMG + off + (uint32_t)(r4 * 4) * 16) = z;                    // df = 0, w = 0
+                    *reinterpret_cast<uint4*>(sbase + 4 * D::A_IMG + off + (uint32_t)(r4 * 4 + 3) * 16) = z;                // df = 2, w = 3
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a_full[s]);
             }
         }
     } else if (warp == 5) {                            // ---- producer: weight stages (one per ci-chunk x tap)
@@ -461,8 +475,8 @@ __global__ void __launch_bounds__(256) ol_head_kernel(const float* __restrict__ 
             const float2 ss = scsh[w * 256 + tid];
             const float* p = raw4 + (size_t)w * 25600 + tid;
             float s = 0.f;
-#pragma unroll 4
-            for (int i = 0; i < 100; ++i) s += silu_acc(fmaf(p[(size_t)i * 256], ss.x, ss.y));
+#pragma unroll 10
+            for (int i = 0; i < 100; ++i) s += silu_fast(fmaf(p[(size_t)i * 256], ss.x, ss.y));
             s_gap[tid] = s / 100.f;
         }
         __syncthreads();
@@ -539,10 +553,10 @@ __global__ void ol_tc_pack_kernel(const float* __restrict__ w, int NOUT, int CIN
 constexpr int kOlCin[4] = {1, 32, 64, 128};
 constexpr int kOlCout[4] = {32, 64, 128, 256};
 constexpr int kOlKt[4] = {7, 5, 5, 3};
-constexpr size_t kStagedPerWindow = 258048;      // max over blocks of (NPAIR*NCC*A_STAGE / WPT)
-static_assert((size_t)OlDer<1>::NPAIR * OlDer<1>::NCC * OlDer<1>::A_STAGE / OlDer<1>::WPT <= kStagedPerWindow, "staged size");
-static_assert((size_t)OlDer<2>::NPAIR * OlDer<2>::NCC * OlDer<2>::A_STAGE / OlDer<2>::WPT <= kStagedPerWindow, "staged size");
-static_assert((size_t)OlDer<3>::NPAIR * OlDer<3>::NCC * OlDer<3>::A_STAGE / OlDer<3>::WPT <= kStagedPerWindow, "staged size");
+constexpr size_t kStagedPerWindow = 86016;       // max over blocks of (NPAIR*NCC*A_GSTAGE / WPT)
+static_assert((size_t)OlDer<1>::NPAIR * OlDer<1>::NCC * OlDer<1>::A_GSTAGE / OlDer<1>::WPT <= kStagedPerWindow, "staged size");
+static_assert((size_t)OlDer<2>::NPAIR * OlDer<2>::NCC * OlDer<2>::A_GSTAGE / OlDer<2>::WPT <= kStagedPerWindow, "staged size");
+static_assert((size_t)OlDer<3>::NPAIR * OlDer<3>::NCC * OlDer<3>::A_GSTAGE / OlDer<3>::WPT <= kStagedPerWindow, "staged size");
 
 template <int L>
 int run_block(CnnOlTc* t, const float* prev, float* out, const float* bias, const int* n_dev, long long n_total, long long base,
@@ -555,7 +569,7 @@ int run_block(CnnOlTc* t, const float* prev, float* out, const float* bias, cons
     SHM_CUDA(cudaFuncSetAttribute(ol_conv_gemm_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::SMEM));
     const long long max_items = (n_chunk + D::WPT - 1) / D::WPT * D::NPAIR;
     const int grid = (int)(max_items < t->nsm ? max_items : t->nsm);
-    ol_conv_gemm_kernel<L><<<grid, 224, D::SMEM, st>>>(a);
+    ol_conv_gemm_kernel<L><<<grid, 256, D::SMEM, st>>>(a);
     SHM_LAUNCH_CHECK();
     return SHM_OK;
 }
