@@ -31,7 +31,7 @@ constexpr int OL_T = 200, OL_F = 4, OL_THREADS = 320;
 constexpr int OL_CIN[4] = {1, 32, 64, 128};
 constexpr int OL_COUT[4] = {32, 64, 128, 256};
 constexpr int OL_KT[4] = {7, 5, 5, 3};
-constexpr int OL_HH[4] = {200, 100, 50, 25};
+// plane heights per block: 200, 100, 50, 25
 constexpr int OL_PLANE_IN = 12800, OL_PLANE_OUT = 25600;
 
 struct CnnOlDev {

@@ -193,3 +193,57 @@ def test_data_parallel_step_two_ranks_gloo(tmp_path):
                         "127.0.0.1", "--master-port", "29533", str(script)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def _write_catman(path, rows):
+    """A catman MD_*.txt look-alike: 36 header lines (T0 on line 13), tab separated, decimal comma, 18 columns."""
+    head = [f"header line {i}" for i in range(36)]               # skipped (skiprows=36) ...
+    head[12] = "T0 = 06.05.2025 09:08:25"
+    head.append("\t".join(f"col{i}" for i in range(18)))         # ... the next line is what pandas takes as column names
+    lines = ["\t".join(r) for r in rows]
+    path.write_text("\n".join(head + lines) + "\n", encoding="cp1252")
+
+
+def test_catman_reader_matches_reference_reader(tmp_path):
+    """shmfast.openlab_frontend.read_catman_columns == import_catman_file + _to_float of the reference
+    (openlab_import.py:33-85, 01_extract_windows_and_labels.py:58-59): decimal comma, cp1252, non-numeric -> NaN,
+    short (bad) lines skipped; compared with the reference's own reader when it is available (build container)."""
+    from shmfast import openlab_frontend as FE
+    rng = np.random.Generator(np.random.PCG64(3))
+    rows = []
+    for i in range(50):
+        vals = [f"{v:.4f}".replace(".", ",") for v in rng.normal(10, 5, size=17)]
+        vals[0] = f"{i * 0.02:.2f}".replace(".", ",")
+        rows.append(vals + ["ok"])
+    rows[7][1] = "n/a"                                   # non-numeric DMS_1 -> NaN
+    rows[9][10] = "-100000,5"                            # obstruction sentinel in LWA_2 (kept by the reader, handled on the device)
+    p = tmp_path / "MD_test.txt"
+    _write_catman(p, rows)
+    got = FE.read_catman_columns(p)
+    assert got.shape == (50, 4) and got.dtype == np.float32
+    assert np.isnan(got[7, 0]) and got[9, 1] == np.float32(-100000.5)
+    want = np.array([[float(r[c].replace(",", ".")) if r[c] != "n/a" else np.nan for c in (1, 10, 11, 13)] for r in rows], np.float32)
+    assert np.array_equal(got, want, equal_nan=True)
+    ref_dir = Path("/root/reference/20250506_openLAB_tests/Codes")
+    if ref_dir.exists():
+        import importlib.util
+        import pandas as pd
+        spec = importlib.util.spec_from_file_location("ref_openlab_import", str(ref_dir / "openlab_import.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        df = mod.import_catman_file(p)
+        ref = np.stack([pd.to_numeric(df[c], errors="coerce").to_numpy(dtype=np.float32) for c in FE.USED_COLUMNS], axis=1)
+        assert np.array_equal(got, ref, equal_nan=True)
+    bad = tmp_path / "MD_bad.txt"
+    bad.write_text("\n".join(f"h{i}" for i in range(40)), encoding="cp1252")       # no T0 on line 13
+    with pytest.raises(ValueError):
+        FE.read_catman_columns(bad)
+
+
+def test_kl_anneal_matches_reference_formula():
+    """shmfast.train.kl_anneal_sigmoid == kl_anneal_sigmoid of 4DOF/Scripts/03_train_vae.py:120-135."""
+    from shmfast import train
+    for epoch in (1, 2, 15, 16, 30, 50):
+        e0, warm = epoch - 1, max(1, int(50 * 0.3))
+        ref = float(1.0 / (1.0 + np.exp(-((e0 - warm) / float(warm)) * 5.0)))
+        assert abs(train.kl_anneal_sigmoid(epoch, 50) - ref) < 1e-15
