@@ -391,7 +391,7 @@ def hybrid_4dof(vae_sd, cnn_sd, Z, eps1, eps2, thr, batch=512, dtype=np.float32)
     for j in range(0, idx.size, batch):
         sel = idx[j:j + batch]
         zb = Z[sel].astype(dtype)
-        recon, _, _ = vae_forward(vae_sd, zb, None if eps2 is None else eps2[j:j + batch], dtype)
+        recon, _, _ = vae_forward(vae_sd, zb, None if eps2 is None else eps2[j:j + sel.size], dtype)
         xin = cnn4dof_inputs(zb, recon)
         logits = cnn4dof_forward(cnn_sd, xin, dtype)
         logits_all[j:j + batch] = logits

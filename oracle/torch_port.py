@@ -122,7 +122,7 @@ def hybrid_4dof(vae: VaePort, cnn: Cnn4dofPort, series: np.ndarray, mean, std, t
     for j in range(0, idx.size, batch):
         sel = idx[j:j + batch]
         zb = torch.tensor(Z[sel], dtype=torch.float32)
-        e = torch.randn((zb.shape[0], vae.mu.out_features)) if eps2 is None else _t(eps2[j:j + batch])
+        e = torch.randn((zb.shape[0], vae.mu.out_features)) if eps2 is None else _t(eps2[j:j + zb.shape[0]])
         xhat, _, _ = vae(zb, e)
         logits = cnn(torch.stack([zb, (zb - xhat) ** 2], dim=1))
         logits_all[j:j + batch] = logits.numpy()

@@ -252,3 +252,26 @@ def test_openlab_frontend_edge_cases():
     xi, rem = O.clean_and_rule(raw[:, 1], 1.0, 65.0, 5)
     assert rem.sum() == 0 and np.allclose(xi[2:-2], np.convolve(raw[:, 1].astype(np.float64), np.ones(5) / 5, "same")[2:-2].astype(np.float32))
     assert O.openlab_extract_run(raw[:150])["n_windows"] == 0
+
+
+def test_hybrid_oracles_accept_full_length_eps2():
+    """eps2[j] belongs to the j-th FLAGGED window: callers (smoke(), bench) pass one row per window and only the first
+    n_flagged are consumed, in both oracles."""
+    import torch
+    from oracle import torch_port as TP
+    N, T, D, Zd = 40, 100, 12, 16
+    vae_sd, cnn_sd = synth.stage_vae_weights("4dof", seed=1, scale=2.0), synth.cnn4dof_weights(seed=1)
+    Zw = synth.windows(N, T, D, seed=2)
+    eps1, eps2 = synth.eps(N, Zd, seed=1), synth.eps(N, Zd, seed=2)
+    s = O.vae_scores_batched(vae_sd, Zw, eps1, 512)
+    thr = float(np.median(s))
+    ref = O.hybrid_4dof(vae_sd, cnn_sd, Zw, eps1, eps2, thr)
+    k = ref["idx"].size
+    assert 0 < k < N
+    ref2 = O.hybrid_4dof(vae_sd, cnn_sd, Zw, eps1, eps2[:k], thr)
+    assert np.array_equal(ref["logits"], ref2["logits"])
+    series = Zw[0]                                          # torch port takes a series: use identity normalisation
+    r = TP.hybrid_4dof(TP.VaePort(vae_sd), TP.Cnn4dofPort(cnn_sd), synth.series(N + T - 1, D, seed=3), np.zeros(D, np.float32),
+                       np.ones(D, np.float32), thr=0.0, eps1=eps1, eps2=eps2)
+    assert r["idx"].size == N and r["logits"].shape == (N, 2)
+    del series, torch
