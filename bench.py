@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["shmfast", "reference"], default="shmfast")
-    ap.add_argument("--workload", choices=["4dof_hybrid", "4dof_score", "openlab_hybrid", "4dof_train"], default="4dof_hybrid")
+    ap.add_argument("--workload", choices=["4dof_hybrid", "4dof_score", "openlab_hybrid", "4dof_train", "1dof_score"], default="4dof_hybrid")
     ap.add_argument("--flag-pct", type=float, default=None, help="percentile of the calibration scores used as gate threshold (default: 4dof 99 = ~1 %% flagged, the 04_vae_thresholding.py rule; openlab 95). 53 / 62 reproduce the repo's real test-set flag rates (47 %% / 38 %%)")
     ap.add_argument("--windows", type=int, default=1 << 20, help="windows per GPU per step")
     ap.add_argument("--engine", choices=["auto", "fp32", "tc"], default="auto")
@@ -674,6 +674,115 @@ def run_train(a):
         dist.destroy_process_group()
 
 
+
+# ----------------------------------------------------------------------------------------------
+# 1_DOF (BASELINE.json configs[0], the reference's CPU-runnable case): standardise + window (T=80, stride 1) -> LSTM-VAE
+# (H=32, L=2, no LayerNorm; fp32 engine) -> reconstruction -> overlap-average stitch, de-standardise, RMSE per 100-sample
+# segment (1_DOF/Scripts/04_test_seen_variants.py:281-311, datasets.py:17-71).
+# ----------------------------------------------------------------------------------------------
+def run_onedof(a):
+    from shmfast import ops, synth
+    from shmfast.shard import max_over_ranks, sum_over_ranks
+    import torch.distributed as dist
+
+    T, D, Z = 80, 12, 5
+    N = min(a.windows, 1 << 18)                               # the reconstruction [N,80,12] is materialised for the stitch
+    rows = N + T - 1
+    rng = np.random.Generator(np.random.PCG64(7))
+    series_h = synth.series(rows, D, seed=5)
+    mean = series_h.mean(axis=0).astype(np.float64)
+    std = series_h.std(axis=0).astype(np.float64) + 1e-8
+    if a.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        from oracle import np_oracle as O, torch_port as TP
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        n = min(a.cpu_sample, N)
+        vae = TP.VaePort(synth.stage_vae_weights("1dof", seed=0))
+        ser = series_h[: n + T - 1]
+        times = []
+        for i in range(a.warmup + a.steps):
+            t0 = time.perf_counter()
+            xn = ((ser - mean) / std).astype(np.float32)
+            W = np.stack([xn[j:j + T] for j in range(n)])
+            with torch.no_grad():
+                rec = vae(torch.from_numpy(W), torch.randn(n, Z))[0].numpy()
+            y = O.destandardize(O.stitch_windows(rec, ser.shape[0], 1), mean, std)
+            O.segment_rmse(ser, y, 100)
+            if i >= a.warmup:
+                times.append(time.perf_counter() - t0)
+        ms = 1e3 * sum(times) / len(times)
+        val = n / (ms / 1e3)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "windows/s", "n_gpus": a.gpus, "steps": a.steps,
+                          "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": {"workload": "1dof_score", "windows_per_step": n},
+                          "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": "port",
+                                           "sample": f"{n} windows per pass: standardise + window + VAE (torch.nn) + stitch + segment RMSE (NumPy)"},
+                          "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", init_method="env://", device_id=dev)
+    vae = ops.VaeScorer(synth.stage_vae_weights("1dof", seed=0), dev)
+    pinned = torch.from_numpy(series_h).pin_memory()
+    series_d = pinned.to(dev)
+    eps = torch.randn((N, Z), device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    buf = {}
+
+    def step(sd_):
+        src = ops.WindowSource(sd_, T, stride=1, mean=mean.astype(np.float32), std=std.astype(np.float32))
+        out = vae.score(src, eps, n=N, want_recon=True, out=buf)
+        return ops.stitch_segment_rmse(out["recon"], rows, 1, mean, std, sd_, 100, want_series=False)[1], out["score"]
+
+    for _ in range(a.warmup):
+        step(series_d)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = []
+    for _ in range(a.steps):
+        flush.zero_()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(); step(series_d); s1.record()
+        ev.append((s0, s1))
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    total_ms = max_over_ranks(sum(x.elapsed_time(y) for x, y in ev), dev)
+    windows_total = sum_over_ranks(float(N * a.steps), dev)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        rm, sc = step(pinned.to(dev, non_blocking=True))
+        rm_h, sc_h = rm.cpu(), sc.cpu()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+    if rank == 0:
+        ms = total_ms / a.steps
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        achieved = FLOP_PER_WINDOW["1dof"] * N / (ms / 1e3) / 1e12
+        print(json.dumps({
+            "metric": METRIC, "value": windows_total / (total_ms / 1e3), "unit": "windows/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "1dof_score", "windows_per_gpu": N, "T": T, "D": D, "H": 32, "Z": Z, "L": 2, "engine": "fp32",
+                       "post": "overlap-average stitch + de-standardise + RMSE per 100-sample segment (fp64)",
+                       "l2": "flushed between timed steps (512 MiB memset)", "parallelism": f"window-range shards x{world}, no collective"},
+            "clocks": clocks,
+            "e2e": {"value": windows_total / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": int(pinned.numel() * 4),
+                    "d2h_bytes_per_step": int(N * 4 + rm_h.numel() * 8), "ms_per_step": 1e3 * e2e_s / a.steps,
+                    "api": "ops.VaeScorer.score(want_recon) + ops.stitch_segment_rmse"},
+            "gpu_launches": 2 * a.steps,
+            "roofline": {"bound": "fp32", "kernel": "vae_score_fp32_kernel<32> (whole step)", "achieved": achieved, "peak": fp32_peak,
+                         "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+                         "peak_source": "derived: 148 SM x 128 FMA lanes x 2 x 1.965 GHz", "algorithmic_flop_per_window": FLOP_PER_WINDOW["1dof"]},
+            "cpu_baseline": None}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     global PCT4
     a = parse_args()
@@ -683,6 +792,8 @@ def main():
         run_openlab(a)
     elif a.workload == "4dof_train":
         run_train(a)
+    elif a.workload == "1dof_score":
+        run_onedof(a)
     elif a.impl == "reference":
         run_reference(a)
     else:
