@@ -742,6 +742,10 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
     if (warp == TC_WARP_MMA) tmem_dealloc(tbase, 512);
 }
 
+}  // namespace shm
+#include "vae_tc_dual.cuh"
+namespace shm {
+
 // ------------------------------------------------------------------------------------------------
 // weight repacking: state_dict fp32 -> pre-scaled bf16 hi|lo stage images in UMMA K-major layout
 //   out, per chunk c: [in part: kt x {hi,lo} images of [128 x KT_in]] [hh part: kt x {hi,lo} of [128 x 64]]
@@ -817,6 +821,8 @@ int vae_tc_alloc(VaeTc* tc, const shm_vae_cfg& cfg) {
     cudaError_t e = cudaSuccess;
     if (cfg.H == 128) e = cudaFuncSetAttribute(vae_score_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::total);
     else e = cudaFuncSetAttribute(vae_score_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64>::total);
+    if (e == cudaSuccess && cfg.H == 64)
+        e = cudaFuncSetAttribute(vae_score_tc_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D2Smem::total);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(vae_score_tc)"); return SHM_ERR_CUDA; }
     tc->H = cfg.H; tc->L = cfg.L; tc->D = cfg.D;
     return SHM_OK;
@@ -883,7 +889,11 @@ int vae_tc_score(VaeTc* tc, const VaeDev& P, const WinSrc& src, const VaeIO& io,
         T.pass[p].sink = (l < L - 1) ? SINK_STREAM : (dec ? SINK_LAST_DEC : SINK_LAST_ENC);
     }
     if (H == 128) vae_score_tc_kernel<128><<<grid, TC_THREADS, TcSmem<128>::total, st>>>(P, T, src, io);
-    else vae_score_tc_kernel<64><<<grid, TC_THREADS, TcSmem<64>::total, st>>>(P, T, src, io);
+    else if (L == 1) {
+        // single-layer H = 64 (the openLAB model): two independent tiles per CTA, see vae_tc_dual.cuh
+        const int grid2 = (int)min((long long)device_sm_count(dev), (tiles + 1) / 2);
+        vae_score_tc_dual_kernel<<<grid2, TC_THREADS, D2Smem::total, st>>>(P, T, src, io);
+    } else vae_score_tc_kernel<64><<<grid, TC_THREADS, TcSmem<64>::total, st>>>(P, T, src, io);
     SHM_LAUNCH_CHECK();
     return SHM_OK;
 }
