@@ -46,6 +46,7 @@ CNN_FLOP_PER_FLAGGED = {"4dof": 4_070_912, "openlab": 133_851_648}
 # ncu --set full capture of vae_score_tc_kernel<128> (profiles/r01_vae_tc_raw.csv): 15.577 GB read + 15.581 GB written
 # for a 151,552-window launch
 NCU_DRAM_BYTES_PER_WINDOW_4DOF = (15.577271e9 + 15.580796e9) / 151552
+NCU_DRAM_BYTES_PER_WINDOW_OPENLAB = (41.604608e6 + 0.883456e6) / 151552      # profiles/r01_vae_tc_dual_raw.csv (algorithmic: 240 + 32 + 4)
 
 
 def parse_args():
@@ -385,9 +386,8 @@ def run_openlab(a):
     from shmfast.shard import max_over_ranks, sum_over_ranks
 
     pct = 95.0 if a.flag_pct is None else a.flag_pct
-    if a.impl == "reference":
-        if int(os.environ.get("RANK", "0")) != 0:
-            return
+    def cpu_port(warmup, steps):
+        """The reference's openLAB wiring (10_test_hybrid_pipeline.py:233-302,351-367) on torch.nn CPU kernels, all host threads."""
         from oracle import torch_port as TP
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
@@ -399,14 +399,19 @@ def run_openlab(a):
         cal = TP.hybrid_openlab(vae, cnn, series[: (min(2000, n) - 1) * 20 + 200], [1, 2, 3], vmu, vsd, cmu, csd, float("inf"), 0.5)
         thr = float(np.percentile(cal["score"], pct))
         times = []
-        for i in range(a.warmup + a.steps):
+        for i in range(warmup + steps):
             t0 = time.perf_counter()
             r = TP.hybrid_openlab(vae, cnn, series, [1, 2, 3], vmu, vsd, cmu, csd, thr, 0.5)
-            if i >= a.warmup:
+            if i >= warmup:
                 times.append(time.perf_counter() - t0)
         ms = 1e3 * sum(times) / len(times)
-        val = n / (ms / 1e3)
         sample = f"{n} windows of the openlab_hybrid step per timed pass (torch.nn CPU kernels, batch 256), flagged {int(r['mask'].sum())}"
+        return n / (ms / 1e3), ms, cores, sample, n
+
+    if a.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        val, ms, cores, sample, n = cpu_port(a.warmup, a.steps)
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "windows/s", "n_gpus": a.gpus, "steps": a.steps,
                           "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f32", "data": "synthetic", "config": {"workload": "openlab_hybrid", "windows_per_step": n},
@@ -501,6 +506,10 @@ def run_openlab(a):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
     if rank == 0:
+        cpu_baseline = None
+        if world == 1 and not a.no_cpu_baseline:
+            val, _, cores, sample, _ = cpu_port(1, 1)
+            cpu_baseline = {"value": val, "unit": "windows/s", "cores": cores, "kind": "port", "sample": sample}
         pk = peaks()
         eng = {ops.ENGINE_FP32: "fp32", ops.ENGINE_TC_BF16X3: "tc_bf16x3"}[vae.engine]
         achieved = FLOP_PER_WINDOW["openlab"] * N / (kern_ms / 1e3) / 1e12
@@ -519,10 +528,13 @@ def run_openlab(a):
                     "api": "shmfast.pipeline.HybridOpenLab.run"},
             "gpu_launches": 3 * a.steps,
             "roofline": {"bound": "tensor", "kernel": "vae_score (fused LSTM-VAE scorer)", "achieved": achieved, "peak": pk["tf_sust"],
-                         "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"], "traffic": None, "kernel_ms": kern_ms,
+                         "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
+                         "traffic": NCU_DRAM_BYTES_PER_WINDOW_OPENLAB * N if vae.engine == ops.ENGINE_TC_BF16X3 else None,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_vae_tc_dual_raw.csv (151,552-window launch) scaled to this launch",
+                         "kernel_ms": kern_ms,
                          "peak_source": pk["source"] + " bf16 dense, sustained", "algorithmic_flop_per_window": FLOP_PER_WINDOW["openlab"],
                          "engine": eng},
-            "cpu_baseline": None}), flush=True)
+            "cpu_baseline": cpu_baseline}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
