@@ -277,38 +277,40 @@ def run_shmfast(a):
     # ---- end to end through the public API with host buffers ----
     e2e = None
     if not a.no_e2e:
-        host_score = torch.empty((N,), dtype=torch.float32).pin_memory()
-        host_pred = torch.empty((N,), dtype=torch.int64).pin_memory()
-        host_p = torch.empty((N,), dtype=torch.float32).pin_memory()
+        from shmfast.stream import HostStream, scatter_flagged
+        outs = {"score": ((N,), torch.float32)}
+        if a.workload == "4dof_hybrid":
+            outs.update(y_pred=((N,), torch.int64), p_struct=((N,), torch.float32), count=((1,), torch.int32))
+        pipe = HostStream(dev, series_pinned.shape, outs)
 
-        def e2e_step():
-            sd_ = series_pinned.to(dev, non_blocking=True)                 # H2D of this step's input
+        def e2e_chunk(sd_, i):                                             # device work of one chunk, current stream, no host sync
             src_ = ops.WindowSource(sd_, T, stride=1, mean=mean, std=std, nan_to_zero=True)
             e1_ = torch.randn((N, Z), device=dev)                          # the reference draws eps on the device too
-            if a.workload == "4dof_hybrid":
-                e2_ = torch.randn((max_flag, Z), device=dev)
-                res = hyb.run(src_, e1_, e2_, n=N)                         # sync_count=True: 4-byte D2H like np.where
-                y_pred, p_full = Hybrid4dof.scatter(res, N)
-                host_pred.copy_(y_pred, non_blocking=True)
-                host_p.copy_(p_full, non_blocking=True)
-            else:
-                res = dict(score=vae.score(src_, e1_, n=N)["score"])
-            host_score.copy_(res["score"], non_blocking=True)
-            torch.cuda.synchronize()
+            if a.workload != "4dof_hybrid":
+                return dict(score=vae.score(src_, e1_, n=N)["score"])
+            e2_ = torch.randn((max_flag, Z), device=dev)
+            res = hyb.run(src_, e1_, e2_, n=N, sync_count=False, max_flagged=max_flag)
+            y_pred, p_full = scatter_flagged(res["idx"], res["count"], N, [res["label"], res["p_struct"]], [torch.int64, torch.float32])
+            return dict(score=res["score"], y_pred=y_pred, p_struct=p_full, count=res["count"].reshape(1))
 
-        e2e_step()
+        def e2e_run(k):                                                    # k chunks: H2D(i+1) and D2H(i-1) run under chunk i's kernels
+            got = 0
+            for _, host in pipe.run((series_pinned for _ in range(k)), e2e_chunk):
+                got += int(host["score"].shape[0])
+            return got
+
+        e2e_run(2)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(a.steps):
-            e2e_step()
+        assert e2e_run(a.steps) == N * a.steps
         torch.cuda.synchronize()
         e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
         d2h = N * 4 + (N * 8 + N * 4 + 4 if a.workload == "4dof_hybrid" else 0)
         e2e = {"value": windows_total / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": int(series_pinned.numel() * 4),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / a.steps,
-               "api": "shmfast.pipeline.Hybrid4dof.run + scatter (host pinned series in, scores/labels/p_struct out)"}
+               "api": "shmfast.stream.HostStream around shmfast.pipeline.Hybrid4dof.run + scatter_flagged (pinned host series in, scores/labels/p_struct out per chunk; copies on side streams under the next chunk's kernels)"}
 
     cpu_baseline = None
     torch_cuda = None
@@ -485,24 +487,28 @@ def run_openlab(a):
     windows_total = sum_over_ranks(float(N * a.steps), dev)
     value = windows_total / (total_ms / 1e3)
 
-    host_score = torch.empty((N,), dtype=torch.float32).pin_memory()
+    from shmfast.stream import HostStream, scatter_flagged
+    pipe = HostStream(dev, pinned.shape, {"score": ((N,), torch.float32), "flag": ((N,), torch.uint8), "pred": ((N,), torch.int64),
+                                          "prob": ((N,), torch.float64), "count": ((1,), torch.int32)})
 
-    def e2e_step():
-        sd_ = pinned.to(dev, non_blocking=True)
+    def e2e_chunk(sd_, i):                                                 # device work of one chunk, current stream, no host sync
         g, r = sources(sd_)
-        res = hyb.run(g, r, torch.randn((N, 8), device=dev), n=N)
-        host_score.copy_(res["score"], non_blocking=True)
-        flags = res["flag"].cpu(); pred = res["pred"].cpu(); prob = res["prob"].cpu()
-        torch.cuda.synchronize()
-        return flags, pred, prob
+        res = hyb.run(g, r, torch.randn((N, 8), device=dev), n=N, sync_count=False, max_flagged=max_flag)
+        pred, prob = scatter_flagged(res["idx"], res["count"], N, [res["pred"], res["prob"]], [torch.int64, torch.float64])
+        return dict(score=res["score"], flag=res["flag"], pred=pred, prob=prob, count=res["count"].reshape(1))
 
-    e2e_step()
+    def e2e_run(k):                                                        # H2D(i+1) and D2H(i-1) run under chunk i's kernels
+        got = 0
+        for _, host in pipe.run((pinned for _ in range(k)), e2e_chunk):
+            got += int(host["score"].shape[0])
+        return got
+
+    e2e_run(2)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        e2e_step()
+    assert e2e_run(a.steps) == N * a.steps
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
     if rank == 0:
@@ -524,8 +530,8 @@ def run_openlab(a):
                        "l2": "flushed between timed steps (512 MiB memset)", "parallelism": f"window-range shards x{world}, no collective"},
             "clocks": clocks,
             "e2e": {"value": windows_total / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": int(pinned.numel() * 4),
-                    "d2h_bytes_per_step": int(N * 4 + N + 16 * n_flag + 4), "ms_per_step": 1e3 * e2e_s / a.steps,
-                    "api": "shmfast.pipeline.HybridOpenLab.run"},
+                    "d2h_bytes_per_step": int(N * (4 + 1 + 8 + 8) + 4), "ms_per_step": 1e3 * e2e_s / a.steps,
+                    "api": "shmfast.stream.HostStream around shmfast.pipeline.HybridOpenLab.run + scatter_flagged (copies on side streams under the next chunk's kernels)"},
             "gpu_launches": 3 * a.steps,
             "roofline": {"bound": "tensor", "kernel": "vae_score (fused LSTM-VAE scorer)", "achieved": achieved, "peak": pk["tf_sust"],
                          "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
