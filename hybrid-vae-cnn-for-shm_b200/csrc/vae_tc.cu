@@ -37,6 +37,8 @@ constexpr int TC_WARP_AUX0 = TC_EPI_WARPS;    // 4 warps: window staging (encode
 constexpr int TC_WARP_PROD = TC_EPI_WARPS + 4, TC_WARP_MMA = TC_EPI_WARPS + 5;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 8) * 32;   // epilogue | staging/output group | copy producer | MMA issuer | 2 idle
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_CLUSTER = 2;                 // CTAs per cluster: each loads half of every weight stage and multicasts it to both
+constexpr int TC_HEADS_SCRATCH = 3 * 16 * 128 * 4;   // per-CTA global scratch of the heads stage (mu | logvar | z), bytes
 constexpr int TC_REG_EPI = 88, TC_REG_AUX = 64;       // setmaxnreg budgets: 16*32*88 + 8*32*64 = 61440 of 65536 registers
 constexpr float NLOG2E = -1.4426950408889634f;
 
@@ -187,6 +189,7 @@ struct PassCtx {
     unsigned char* wo_img;       // W_o fp16 hi|lo K-major images (B operand of the output Linear)
     float* bo_s;
     unsigned char* scratch;
+    float* heads_scratch;
     uint32_t t_acc, t_h;
     int T, nvalid, hT_buf, u_buf;
     long long n0;
@@ -270,7 +273,7 @@ __device__ __forceinline__ void mma_part(TcBars* bars, uint32_t ring_a, uint32_t
                         if (half == 0) mma_ss(acc, kdesc(a_lo + k * 4096), bdesc, IDESC, 1u);
                     }
                 }
-                mma_commit(&bars->w_empty[slot]);
+                mma_commit_mc(&bars->w_empty[slot], (uint16_t)((1u << TC_CLUSTER) - 1));   // the slot is refilled by BOTH producers
             }
             __syncwarp();
             accf = 1u;
@@ -399,12 +402,18 @@ __device__ __forceinline__ void prod_pass(const PassCtx& pc, const unsigned char
     const int T = pc.T;
     const int part_in_bytes = (in_kind == IN_X) ? 2 * TC_XSTAGE : KT_PER_PART * 2 * TC_STAGE;
     const int part_hh_bytes = KT_PER_PART * 2 * TC_STAGE;
+    // Every CTA of the cluster consumes the same weight stream in the same order: each loads 1/TC_CLUSTER of a stage and
+    // multicasts it into the same ring slot of all of them (one L2 read per cluster instead of one per CTA).  A slot is
+    // free when the MMA issuers of ALL CTAs have committed it (w_empty counts TC_CLUSTER multicast commits).
+    const uint32_t crank = cluster_ctarank();
     auto load_part = [&](const unsigned char* g, int nstage, uint32_t bytes) {
+        const uint32_t part = bytes / TC_CLUSTER;
         for (int s = 0; s < nstage; ++s) {
             const uint32_t slot = ring_it % TC_NST;
             mbar_wait(&bars->w_empty[slot], ((ring_it / TC_NST) & 1) ^ 1);
             mbar_arrive_expect_tx(&bars->w_full[slot], bytes);
-            bulk_g2s(pc.ring + slot * TC_STAGE, g + (size_t)s * bytes, bytes, &bars->w_full[slot]);
+            bulk_g2s_mc(pc.ring + slot * TC_STAGE + crank * part, g + (size_t)s * bytes + crank * part, part, &bars->w_full[slot],
+                        (uint16_t)((1u << TC_CLUSTER) - 1));
             ++ring_it;
         }
     };
@@ -539,7 +548,9 @@ __device__ __forceinline__ void heads_stage(const PassCtx& pc, const VaeDev& P, 
     const int nvalid = pc.nvalid;
     const long long n0 = pc.n0;
     float* hT = reinterpret_cast<float*>(pc.inbuf + pc.hT_buf * S::IMG);      // [H][128] fp32
-    float* muS = reinterpret_cast<float*>(pc.ring);                           // [2Z][128]
+    // [2Z][128] in a per-CTA GLOBAL scratch: the weight ring cannot be borrowed here, the peer CTA's producer may already be
+    // multicasting the next pass's first stages into it
+    float* muS = pc.heads_scratch;
     float* zS = muS + 2 * VAE_MAX_Z * TCM;                                    // [Z][128]
     if (P.has_ln) {
         if (tid < TCM) {
@@ -595,7 +606,7 @@ __device__ __forceinline__ void heads_stage(const PassCtx& pc, const VaeDev& P, 
 }
 
 template <int H>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS, 1)
 vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
     using S = TcSmem<H>;
     constexpr int NCH = S::NCH;
@@ -614,7 +625,7 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
     const int n_tiles = (int)((n_eff + TCM - 1) / TCM);
 
     if (tid == 0) {
-        for (int i = 0; i < TC_NST; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+        for (int i = 0; i < TC_NST; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], TC_CLUSTER); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 1);
             mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], TC_EPI_WARPS);
@@ -637,14 +648,19 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
+    cluster_sync_all();                 // every CTA's mbarriers are initialised before a peer multicasts / commits into them
     tc_fence_after_sync();
     const uint32_t tbase = *tmem_holder;
+    // the CTAs of a cluster run in lock step over the weight stream: same number of tile iterations, dummy tiles
+    // (nvalid = 0) where a CTA has no tile left
+    const int n_iter = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
 
     PassCtx pc;
     pc.bars = bars; pc.ring = smem + S::off_ring; pc.inbuf = smem + S::off_in;
     pc.bias_s = reinterpret_cast<float*>(smem + S::off_bias);
     pc.wo_img = smem + S::off_wo; pc.bo_s = bo_s;
-    pc.scratch = TC.scratch + (size_t)blockIdx.x * TC.scratch_stride;
+    pc.scratch = TC.scratch + (size_t)blockIdx.x * (TC.scratch_stride + TC_HEADS_SCRATCH);
+    pc.heads_scratch = reinterpret_cast<float*>(pc.scratch + TC.scratch_stride);
     pc.t_acc = tbase;                  // 2 x 128 accumulator columns
     pc.t_h = tbase + 256;              // 2 x H columns: h_t as fp16 pairs, [hi H/2 | lo H/2]
     pc.T = T;
@@ -681,9 +697,10 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
     // producer / MMA / staging warpgroup drops to 88.  CTA-wide phases meet at barrier 0.
     if (warp < TC_EPI_WARPS) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REG_EPI));
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            pc.n0 = (long long)tile * TCM;
-            pc.nvalid = (int)min((long long)TCM, n_eff - pc.n0);
+        for (int it = 0; it < n_iter; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            pc.n0 = tile < n_tiles ? (long long)tile * TCM : 0;
+            pc.nvalid = tile < n_tiles ? (int)min((long long)TCM, n_eff - pc.n0) : 0;
             pc.hT_buf = 1;                         // in-buffer that receives the encoder's fp32 h_T
             for (int p = 0; p < TC.n_pass; ++p) {
                 int in_kind, sink;
@@ -703,9 +720,10 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
         }
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REG_AUX));
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            pc.n0 = (long long)tile * TCM;
-            pc.nvalid = (int)min((long long)TCM, n_eff - pc.n0);
+        for (int it = 0; it < n_iter; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            pc.n0 = tile < n_tiles ? (long long)tile * TCM : 0;
+            pc.nvalid = tile < n_tiles ? (int)min((long long)TCM, n_eff - pc.n0) : 0;
             pc.hT_buf = 1;
             for (int p = 0; p < TC.n_pass; ++p) {
                 int in_kind, sink;
@@ -739,6 +757,7 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
     }
     tc_fence_before_sync();
     __syncthreads();
+    cluster_sync_all();                 // no CTA leaves while a peer can still write into its shared memory
     if (warp == TC_WARP_MMA) tmem_dealloc(tbase, 512);
 }
 
@@ -864,10 +883,11 @@ int vae_tc_score(VaeTc* tc, const VaeDev& P, const WinSrc& src, const VaeIO& io,
     SHM_CUDA(cudaGetDevice(&dev));
     const int H = tc->H, L = tc->L;
     const long long tiles = (io.n + TCM - 1) / TCM;
-    const int grid = (int)min((long long)device_sm_count(dev), tiles);
+    int grid = (int)min((long long)device_sm_count(dev), tiles);
+    grid = (grid + TC_CLUSTER - 1) / TC_CLUSTER * TC_CLUSTER;           // whole clusters; surplus CTAs run dummy tiles
     const size_t img = (size_t)TCM * H * 2 * 2;
     const size_t stride = (L > 1) ? img * (size_t)src.T : 0;
-    const size_t need = stride * (size_t)device_sm_count(dev);
+    const size_t need = (stride + TC_HEADS_SCRATCH) * (size_t)(device_sm_count(dev) + TC_CLUSTER);
     if (need > tc->scratch_bytes) {
         SHM_CUDA(cudaStreamSynchronize(st));
         if (tc->scratch) cudaFree(tc->scratch);

@@ -459,6 +459,7 @@ vae_score_tc_dual_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
             for (int tl = 0; tl < D2_NT; ++tl) {           // heads, one tile after the other
                 PassCtx pc;
                 pc.ring = cx.smem0; pc.inbuf = cx.smem0;           // buffers addressed in 32 KB units from unit 0
+                pc.heads_scratch = reinterpret_cast<float*>(cx.smem0);          // mu | logvar | z scratch: unit 0 (the encoder weights are dead)
                 pc.hT_buf = d2_hT_unit(tl); pc.u_buf = 4 + tl;
                 pc.nvalid = cx.nvalid[tl]; pc.n0 = cx.n0[tl];
                 heads_stage<D2_H>(pc, P, io);
