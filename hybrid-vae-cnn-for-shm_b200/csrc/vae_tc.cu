@@ -42,7 +42,10 @@ constexpr int TC_HEADS_SCRATCH = 3 * 16 * 128 * 4;   // per-CTA global scratch o
 constexpr int TC_REG_EPI = 88, TC_REG_AUX = 64;       // setmaxnreg budgets: 16*32*88 + 8*32*64 = 61440 of 65536 registers
 constexpr float NLOG2E = -1.4426950408889634f;
 
-enum { IN_X = 0, IN_STREAM = 1, IN_CONST = 2 };
+enum { IN_X = 0, IN_STREAM = 1, IN_CONST = 2, IN_HOIST = 3 };
+// IN_HOIST: the layer input is constant over time (decoder layer 0: u = tanh(W z + b) repeated T times, temporal_vae.py:65-70), so its
+// projection G = u W_ih^T + b is computed ONCE per tile (one MMA sweep, drained to a per-CTA global image) and each step's cell update
+// adds its chunk of G, streamed back through the two idle input buffers, instead of the bias: the pass issues half the MMAs.
 enum { SINK_STREAM = 0, SINK_LAST_ENC = 1, SINK_LAST_DEC = 2 };
 
 struct TcPassDev {
@@ -55,6 +58,7 @@ struct TcDev {
     int n_pass, L;
     unsigned char* scratch;     // per-CTA h_t stream: [grid][T][hi|lo image]
     unsigned long long scratch_stride;
+    unsigned long long g_bytes; // per-CTA image of the hoisted input projection (IN_HOIST), 0 if unused
     long long* dbg;             // optional [grid][8] profiling counters
 };
 
@@ -75,6 +79,7 @@ struct TcSmem {
 
 struct TcBars {
     uint64_t w_full[TC_NST], w_empty[TC_NST], in_full[2], in_empty[2], acc_full[2], acc_empty[2], h_full[2], xhat_full, xhat_empty;
+    uint64_t g_full[2], g_empty[2];     // IN_HOIST: chunk images of G in the two input buffers
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -125,8 +130,9 @@ struct EpiCtx {
     const float* bias_s;
     unsigned char* img;          // scratch image of this step (SINK_STREAM)
     float* hT;                   // fp32 h_T [H][128] (SINK_LAST_ENC)
+    const unsigned char* gs;     // input buffers carrying G chunk images [32 units][128 rows][4 gates] fp32 (HOIST)
     int wg, row, lane;
-    bool last_step;
+    bool last_step, first_step;
     long long* prof;
 };
 
@@ -135,8 +141,8 @@ struct EpiCtx {
 // `c` is a RUN-TIME chunk index: the chunk loop is a real loop (the cell state rotates through the register arrays),
 // so the hot loop of the epilogue is ~11 KB of code instead of ~41 KB -- the fully unrolled form overflowed the 32 KB
 // L1.5 instruction cache (ncu: 25 % of the epilogue's issue slots were stall_no_inst).
-template <int H, int SINK>
-__device__ __forceinline__ void epi_chunk(const EpiCtx& x, int c, uint32_t acc_parity, float (&cst)[TC_UPT]) {
+template <int H, int SINK, bool HOIST>
+__device__ __forceinline__ void epi_chunk(const EpiCtx& x, int c, uint32_t acc_parity, uint32_t g_parity, float (&cst)[TC_UPT]) {
     using S = TcSmem<H>;
     static_assert(TC_UPT == 8, "one batch of 8 units per thread per chunk");
     const int b = c & 1;
@@ -158,11 +164,28 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& x, int c, uint32_t acc_p
     __syncwarp();
     if (x.lane == 0) mbar_arrive(&x.bars->acc_empty[b]);
     float hv[8];
+    if (HOIST) {
+        if (x.first_step) {                                          // h_{-1} = 0: no MMA was issued, the accumulator is stale
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const float4 bb = *reinterpret_cast<const float4*>(x.bias_s + (u0 + u) * 4);
-        lstm_cell(__uint_as_float(g0[u]) + bb.x, __uint_as_float(g1[u]) + bb.y, __uint_as_float(g2[u]) + bb.z,
-                  __uint_as_float(g3[u]) + bb.w, cst[u], hv[u]);
+            for (int u = 0; u < 8; ++u) { g0[u] = 0u; g1[u] = 0u; g2[u] = 0u; g3[u] = 0u; }
+        }
+        mbar_wait(&x.bars->g_full[b], g_parity);                    // this chunk's G image has landed in input buffer b
+        const float4* G = reinterpret_cast<const float4*>(x.gs + b * S::IMG) + (x.wg * 8) * TCM + x.row;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 bb = G[u * TCM];                            // u W_ih^T + b for (row, unit u0+u): gates i,f,g,o
+            lstm_cell(__uint_as_float(g0[u]) + bb.x, __uint_as_float(g1[u]) + bb.y, __uint_as_float(g2[u]) + bb.z,
+                      __uint_as_float(g3[u]) + bb.w, cst[u], hv[u]);
+        }
+        __syncwarp();
+        if (x.lane == 0) mbar_arrive(&x.bars->g_empty[b]);
+    } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 bb = *reinterpret_cast<const float4*>(x.bias_s + (u0 + u) * 4);
+            lstm_cell(__uint_as_float(g0[u]) + bb.x, __uint_as_float(g1[u]) + bb.y, __uint_as_float(g2[u]) + bb.z,
+                      __uint_as_float(g3[u]) + bb.w, cst[u], hv[u]);
+        }
     }
     uint32_t hi[4], lo[4];
 #pragma unroll
@@ -190,15 +213,16 @@ struct PassCtx {
     float* bo_s;
     unsigned char* scratch;
     float* heads_scratch;
+    unsigned char* gbuf;         // global image of G, [NCH][32 units][128 rows][4 gates] fp32 (IN_HOIST)
     uint32_t t_acc, t_h;
     int T, nvalid, hT_buf, u_buf;
     long long n0;
 };
 
 // ------------------------------------------------------------------------------------------------ epilogue warps
-template <int H, int SINK>
+template <int H, int SINK, bool HOIST = false>
 __device__ __forceinline__ void epi_pass(const PassCtx& pc, const VaeDev& P, const WinSrc& src, const VaeIO& io, const float* bias_g,
-                                      Cnt2 acc_cnt, long long (&prof)[8]) {
+                                      Cnt2 acc_cnt, long long (&prof)[8], Cnt2 g_cnt = Cnt2{0, 0}) {
     using S = TcSmem<H>;
     constexpr int NCH = S::NCH;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -213,16 +237,18 @@ __device__ __forceinline__ void epi_pass(const PassCtx& pc, const VaeDev& P, con
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int u = 0; u < TC_UPT; ++u) cst[c][u] = 0.f;
-    uint32_t nacc0 = acc_cnt.n0, nacc1 = acc_cnt.n1;
+    uint32_t nacc0 = acc_cnt.n0, nacc1 = acc_cnt.n1, ng0 = g_cnt.n0, ng1 = g_cnt.n1;
     for (int t = 0; t < T; ++t) {
         const uint32_t hbuf = pc.t_h + (uint32_t)((t & 1) * H);
         EpiCtx ctx{pc.bars, pc.t_acc, hbuf, lane_base, pc.bias_s, pc.scratch + (size_t)t * S::IMG,
-                   reinterpret_cast<float*>(pc.inbuf + pc.hT_buf * S::IMG), wg, row, lane, t == T - 1, prof};
+                   reinterpret_cast<float*>(pc.inbuf + pc.hT_buf * S::IMG), pc.inbuf, wg, row, lane, t == T - 1, t == 0, prof};
 #pragma unroll 1
         for (int c = 0; c < NCH; ++c) {
             const uint32_t par = ((c & 1) ? nacc1 : nacc0) & 1;
             if (c & 1) ++nacc1; else ++nacc0;
-            epi_chunk<H, SINK>(ctx, c, par, cst[0]);
+            const uint32_t gpar = ((c & 1) ? ng1 : ng0) & 1;
+            if (HOIST) { if (c & 1) ++ng1; else ++ng0; }
+            epi_chunk<H, SINK, HOIST>(ctx, c, par, gpar, cst[0]);
             if constexpr (NCH > 1) {                           // rotate the cell state: chunk c+1's state moves to cst[0]
 #pragma unroll
                 for (int u = 0; u < TC_UPT; ++u) {
@@ -239,6 +265,46 @@ __device__ __forceinline__ void epi_pass(const PassCtx& pc, const VaeDev& P, con
         if (lane == 0) mbar_arrive(&pc.bars->h_full[t & 1]);
     }
     if (SINK == SINK_STREAM) fence_proxy_async_all();          // scratch writes -> visible to the bulk-copy engine
+}
+
+// IN_HOIST, once per tile: drain G = u W_ih^T (+ b) chunk by chunk from the accumulators into the per-CTA global image
+// [chunk][32 units][128 rows][4 gates] fp32 -- the layout the cell update reads back from shared memory (one float4 per row and unit).
+template <int H>
+__device__ __forceinline__ void epi_hoist_pre(const PassCtx& pc, const float* bias_g, Cnt2 acc_cnt) {
+    using S = TcSmem<H>;
+    constexpr int NCH = S::NCH;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wg = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    for (int i = tid; i < H * 4; i += TC_EPI_THREADS) pc.bias_s[i] = __ldg(bias_g + i);
+    epi_bar_sync();
+    uint32_t nacc0 = acc_cnt.n0, nacc1 = acc_cnt.n1;
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+        const int b = c & 1;
+        mbar_wait(&pc.bars->acc_full[b], ((c & 1) ? nacc1 : nacc0) & 1);
+        if (c & 1) ++nacc1; else ++nacc0;
+        tc_fence_after_sync();
+        uint32_t g0[8], g1[8], g2[8], g3[8];
+        const uint32_t abase = pc.t_acc + lane_base + (uint32_t)(b * 128 + wg * 8);
+        tmem_ld8(abase + 0, g0);
+        tmem_ld8(abase + 32, g1);
+        tmem_ld8(abase + 64, g2);
+        tmem_ld8(abase + 96, g3);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pc.bars->acc_empty[b]);
+        float4* G = reinterpret_cast<float4*>(pc.gbuf + (size_t)c * S::IMG) + (wg * 8) * TCM + row;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 bb = *reinterpret_cast<const float4*>(pc.bias_s + (c * 32 + wg * 8 + u) * 4);
+            G[u * TCM] = make_float4(__uint_as_float(g0[u]) + bb.x, __uint_as_float(g1[u]) + bb.y, __uint_as_float(g2[u]) + bb.z,
+                                     __uint_as_float(g3[u]) + bb.w);
+        }
+    }
+    fence_proxy_async_all();                                   // the image is read back by bulk copies
 }
 
 // ------------------------------------------------------------------------------------------------ MMA issuer warp
@@ -390,6 +456,61 @@ __device__ __forceinline__ void mma_pass(const PassCtx& pc, uint32_t ring_it, Cn
     }
 }
 
+// IN_HOIST: (1) once per tile, the input projection of every chunk into the accumulators (drained by epi_hoist_pre) ...
+template <int H>
+__device__ __forceinline__ uint32_t mma_hoist_pre(const PassCtx& pc, uint32_t ring_it, Cnt2& n_acc, long long (&prof)[8]) {
+    using S = TcSmem<H>;
+    TcBars* bars = pc.bars;
+    const bool leader = (threadIdx.x & 31) == 0;
+    const uint32_t ring_a = __shfl_sync(0xffffffffu, smem_u32(pc.ring), 0);
+    const uint32_t in_a = __shfl_sync(0xffffffffu, smem_u32(pc.inbuf), 0);
+    const uint32_t t_acc = __shfl_sync(0xffffffffu, pc.t_acc, 0);
+    const int u_buf = __shfl_sync(0xffffffffu, pc.u_buf, 0);
+    ring_it = __shfl_sync(0xffffffffu, ring_it, 0);
+    const uint32_t a_hi = in_a + u_buf * S::IMG, a_lo = a_hi + S::IMGH;
+#pragma unroll 1
+    for (int c = 0; c < S::NCH; ++c) {
+        TC_TWAIT(2, &bars->acc_empty[c & 1], (n_acc.get(c & 1) & 1) ^ 1);
+        n_acc.inc(c & 1);
+        tc_fence_after_sync();
+        mma_part<H, 0>(bars, ring_a, ring_it, t_acc + (uint32_t)((c & 1) * 128), a_hi, a_lo, 0u, prof, leader);
+        if (elect_one()) mma_commit(&bars->acc_full[c & 1]);
+        __syncwarp();
+    }
+    return ring_it;
+}
+
+// ... (2) per step only the recurrent part, starting the accumulator afresh (first_acc = 0); at t = 0 there is nothing to issue.
+template <int H>
+__device__ __forceinline__ void mma_pass_hoist(const PassCtx& pc, uint32_t ring_it, Cnt2 n_acc, Cnt2 n_h, long long (&prof)[8]) {
+    using S = TcSmem<H>;
+    TcBars* bars = pc.bars;
+    const bool leader = (threadIdx.x & 31) == 0;
+    const uint32_t ring_a = __shfl_sync(0xffffffffu, smem_u32(pc.ring), 0);
+    const uint32_t t_acc = __shfl_sync(0xffffffffu, pc.t_acc, 0);
+    const uint32_t t_h = __shfl_sync(0xffffffffu, pc.t_h, 0);
+    ring_it = __shfl_sync(0xffffffffu, ring_it, 0);
+    const int T = __shfl_sync(0xffffffffu, pc.T, 0);
+    for (int t = 0; t < T; ++t) {
+        const uint32_t h_hi = t_h + (uint32_t)(((t - 1) & 1) * H), h_lo = h_hi + H / 2;
+        if (t > 0) {
+            TC_TWAIT(3, &bars->h_full[(t - 1) & 1], n_h.get((t - 1) & 1) & 1);
+            n_h.inc((t - 1) & 1);
+            tc_fence_after_sync();
+        }
+#pragma unroll
+        for (int c = 0; c < S::NCH; ++c) {
+            TC_TWAIT(2, &bars->acc_empty[c & 1], (n_acc.get(c & 1) & 1) ^ 1);
+            n_acc.inc(c & 1);
+            tc_fence_after_sync();
+            if (t > 0) mma_part<H, 2>(bars, ring_a, ring_it, t_acc + (uint32_t)((c & 1) * 128), h_hi, h_lo, 0u, prof, leader);
+            if (elect_one()) mma_commit(&bars->acc_full[c & 1]);
+            __syncwarp();
+        }
+    }
+    mbar_wait(&bars->h_full[(T - 1) & 1], n_h.get((T - 1) & 1) & 1);      // phase bookkeeping, as in mma_pass
+}
+
 // ------------------------------------------------------------------------------------------------ copy producer (one lane)
 template <int H>
 __device__ __forceinline__ void prod_pass(const PassCtx& pc, const unsigned char* w, int in_kind, bool lastdec, uint32_t ring_it,
@@ -440,6 +561,45 @@ __device__ __forceinline__ void prod_pass(const PassCtx& pc, const unsigned char
             if (t > 0) load_part(w + c * chunk_bytes + part_in_bytes, KT_PER_PART * 2, TC_STAGE);
         }
     }
+}
+
+// IN_HOIST producer: (pre) the input-part weight stages of every chunk, once per tile; (main) per step and chunk the chunk's G image
+// into input buffer c & 1 (this CTA's own data: plain bulk copies) and, from the second step on, its recurrent weight stages.
+template <int H>
+__device__ __forceinline__ uint32_t prod_hoist(const PassCtx& pc, const unsigned char* w, uint32_t ring_it, bool pre, Cnt2 n_g) {
+    using S = TcSmem<H>;
+    constexpr int NCH = S::NCH;
+    constexpr int KT_PER_PART = H / 64;
+    TcBars* bars = pc.bars;
+    const int part_bytes = KT_PER_PART * 2 * TC_STAGE;         // input part == recurrent part: [128 x H] hi|lo per chunk
+    const size_t chunk_bytes = (size_t)2 * part_bytes;
+    const uint32_t crank = cluster_ctarank();
+    auto load_part = [&](const unsigned char* g) {
+        const uint32_t part = TC_STAGE / TC_CLUSTER;
+        for (int s = 0; s < KT_PER_PART * 2; ++s) {
+            const uint32_t slot = ring_it % TC_NST;
+            mbar_wait(&bars->w_empty[slot], ((ring_it / TC_NST) & 1) ^ 1);
+            mbar_arrive_expect_tx(&bars->w_full[slot], TC_STAGE);
+            bulk_g2s_mc(pc.ring + slot * TC_STAGE + crank * part, g + (size_t)s * TC_STAGE + crank * part, part, &bars->w_full[slot],
+                        (uint16_t)((1u << TC_CLUSTER) - 1));
+            ++ring_it;
+        }
+    };
+    if (pre) {
+        for (int c = 0; c < NCH; ++c) load_part(w + c * chunk_bytes);
+        return ring_it;
+    }
+    for (int t = 0; t < pc.T; ++t)
+        for (int c = 0; c < NCH; ++c) {
+            const int b = c & 1;
+            mbar_wait(&bars->g_empty[b], (n_g.get(b) & 1) ^ 1);
+            n_g.inc(b);
+            mbar_arrive_expect_tx(&bars->g_full[b], (uint32_t)S::IMG);
+            const unsigned char* g = pc.gbuf + (size_t)c * S::IMG;
+            for (int q = 0; q < S::IMG / 16384; ++q) bulk_g2s(pc.inbuf + b * S::IMG + q * 16384, g + q * 16384, 16384, &bars->g_full[b]);
+            if (t > 0) load_part(w + c * chunk_bytes + part_bytes);
+        }
+    return ring_it;
 }
 
 // ------------------------------------------------------------------------------------------------ staging / output group (warps 8-11)
@@ -629,6 +789,7 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 1);
             mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], TC_EPI_WARPS);
+            mbar_init(&bars->g_full[i], 1); mbar_init(&bars->g_empty[i], TC_EPI_WARPS);
             mbar_init(&bars->h_full[i], TC_EPI_WARPS);
         }
         mbar_init(&bars->xhat_full, 1); mbar_init(&bars->xhat_empty, 4);
@@ -659,8 +820,9 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
     pc.bars = bars; pc.ring = smem + S::off_ring; pc.inbuf = smem + S::off_in;
     pc.bias_s = reinterpret_cast<float*>(smem + S::off_bias);
     pc.wo_img = smem + S::off_wo; pc.bo_s = bo_s;
-    pc.scratch = TC.scratch + (size_t)blockIdx.x * (TC.scratch_stride + TC_HEADS_SCRATCH);
+    pc.scratch = TC.scratch + (size_t)blockIdx.x * (TC.scratch_stride + TC_HEADS_SCRATCH + TC.g_bytes);
     pc.heads_scratch = reinterpret_cast<float*>(pc.scratch + TC.scratch_stride);
+    pc.gbuf = pc.scratch + TC.scratch_stride + TC_HEADS_SCRATCH;
     pc.t_acc = tbase;                  // 2 x 128 accumulator columns
     pc.t_h = tbase + 256;              // 2 x H columns: h_t as fp16 pairs, [hi H/2 | lo H/2]
     pc.T = T;
@@ -669,7 +831,7 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
     // advances them analytically at the end of each pass, so roles that skip a barrier in one pass
     // still know its phase in the next; inside a pass each role counts its own uses from the base.
     uint32_t ring_base = 0;
-    Cnt2 in_base{0, 0}, acc_base{0, 0}, h_base{0, 0};
+    Cnt2 in_base{0, 0}, acc_base{0, 0}, h_base{0, 0}, g_base{0, 0};
     uint32_t xhat_base = 0;
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -679,12 +841,25 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
         if (sink == SINK_LAST_ENC) pc.hT_buf = (in_kind == IN_STREAM) ? (T & 1) : 1;
         pc.u_buf = pc.hT_buf ^ 1;
     };
+    // IN_HOIST runs a one-sweep precompute (input parts only, one accumulator use per chunk) in front of the pass proper
+    auto hoist_pre_advance = [&](uint32_t& ring, Cnt2& acc) {
+        ring += (uint32_t)NCH * KT_PER_PART * 2;
+        acc.n0 += (NCH + 1) / 2;
+        acc.n1 += NCH / 2;
+    };
     auto pass_advance = [&](int in_kind, int sink) {
-        const uint32_t stages_step0 = (uint32_t)NCH * ((in_kind == IN_X) ? 2 : KT_PER_PART * 2);
-        const uint32_t stages_step = stages_step0 + (uint32_t)NCH * KT_PER_PART * 2;
-        ring_base += stages_step0 + (uint32_t)(T - 1) * stages_step;
         const uint32_t even = (uint32_t)((T + 1) / 2), odd = (uint32_t)(T / 2);
-        if (in_kind != IN_CONST) { in_base.n0 += even; in_base.n1 += odd; }
+        if (in_kind == IN_HOIST) {
+            hoist_pre_advance(ring_base, acc_base);
+            ring_base += (uint32_t)(T - 1) * NCH * KT_PER_PART * 2;
+            g_base.n0 += (uint32_t)T * ((NCH + 1) / 2);
+            g_base.n1 += (uint32_t)T * (NCH / 2);
+        } else {
+            const uint32_t stages_step0 = (uint32_t)NCH * ((in_kind == IN_X) ? 2 : KT_PER_PART * 2);
+            const uint32_t stages_step = stages_step0 + (uint32_t)NCH * KT_PER_PART * 2;
+            ring_base += stages_step0 + (uint32_t)(T - 1) * stages_step;
+        }
+        if (in_kind != IN_CONST && in_kind != IN_HOIST) { in_base.n0 += even; in_base.n1 += odd; }
         acc_base.n0 += (uint32_t)T * ((NCH + 1) / 2);
         acc_base.n1 += (uint32_t)T * (NCH / 2);
         h_base.n0 += even; h_base.n1 += odd;
@@ -709,7 +884,14 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
                 cta_sync();                        // (A) previous pass / heads complete and visible
                 if (p == TC.L && encode_only_call) break;
                 const long long pass_t0 = clock64();
-                if (sink == SINK_STREAM) epi_pass<H, SINK_STREAM>(pc, P, src, io, TC.pass[p].bias, acc_base, prof);
+                if (in_kind == IN_HOIST) {
+                    epi_hoist_pre<H>(pc, TC.pass[p].bias, acc_base);
+                    cta_sync();                    // (A2) G is in global memory and the u image is dead: the input buffers now stage G
+                    uint32_t ring_dummy = 0;
+                    Cnt2 acc2 = acc_base;
+                    hoist_pre_advance(ring_dummy, acc2);
+                    epi_pass<H, SINK_STREAM, true>(pc, P, src, io, TC.pass[p].bias, acc2, prof, g_base);
+                } else if (sink == SINK_STREAM) epi_pass<H, SINK_STREAM>(pc, P, src, io, TC.pass[p].bias, acc_base, prof);
                 else if (sink == SINK_LAST_ENC) epi_pass<H, SINK_LAST_ENC>(pc, P, src, io, TC.pass[p].bias, acc_base, prof);
                 else epi_pass<H, SINK_LAST_DEC>(pc, P, src, io, TC.pass[p].bias, acc_base, prof);
                 { const long long _d = clock64() - pass_t0; const int _q = p & 3;
@@ -730,7 +912,22 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
                 pass_setup(p, in_kind, sink);
                 cta_sync();                        // (A)
                 if (p == TC.L && encode_only_call) break;
-                if (warp == TC_WARP_PROD) {
+                if (in_kind == IN_HOIST) {
+                    uint32_t ring2 = ring_base;
+                    Cnt2 acc2 = acc_base;
+                    hoist_pre_advance(ring2, acc2);
+                    if (warp == TC_WARP_PROD) { if (lane == 0) prod_hoist<H>(pc, TC.pass[p].w, ring_base, true, g_base); }
+                    else if (warp == TC_WARP_MMA) { Cnt2 a = acc_base; mma_hoist_pre<H>(pc, ring_base, a, prof); }
+                    __syncwarp();
+                    cta_sync();                    // (A2)
+                    if (warp == TC_WARP_PROD) { if (lane == 0) prod_hoist<H>(pc, TC.pass[p].w, ring2, false, g_base); }
+                    else if (warp == TC_WARP_MMA) {
+                        const long long pass_t0 = clock64();
+                        mma_pass_hoist<H>(pc, ring2, acc2, h_base, prof);
+                        { const long long _d = clock64() - pass_t0; const int _q = p & 3;
+                          if (_q == 0) prof[4] += _d; else if (_q == 1) prof[5] += _d; else if (_q == 2) prof[6] += _d; else prof[7] += _d; }
+                    }
+                } else if (warp == TC_WARP_PROD) {
                     if (lane == 0) prod_pass<H>(pc, TC.pass[p].w, in_kind, sink == SINK_LAST_DEC, ring_base, in_base);
                 } else if (warp == TC_WARP_MMA) {
                     const long long pass_t0 = clock64();
@@ -887,7 +1084,9 @@ int vae_tc_score(VaeTc* tc, const VaeDev& P, const WinSrc& src, const VaeIO& io,
     grid = (grid + TC_CLUSTER - 1) / TC_CLUSTER * TC_CLUSTER;           // whole clusters; surplus CTAs run dummy tiles
     const size_t img = (size_t)TCM * H * 2 * 2;
     const size_t stride = (L > 1) ? img * (size_t)src.T : 0;
-    const size_t need = (stride + TC_HEADS_SCRATCH) * (size_t)(device_sm_count(dev) + TC_CLUSTER);
+    const bool hoist = (H == 128 && L > 1);                   // G chunk image (32 units x 128 rows x 4 gates fp32) must equal an input buffer
+    const size_t g_bytes = hoist ? (size_t)4 * H * TCM * sizeof(float) : 0;
+    const size_t need = (stride + TC_HEADS_SCRATCH + g_bytes) * (size_t)(device_sm_count(dev) + TC_CLUSTER);
     if (need > tc->scratch_bytes) {
         SHM_CUDA(cudaStreamSynchronize(st));
         if (tc->scratch) cudaFree(tc->scratch);
@@ -898,14 +1097,14 @@ int vae_tc_score(VaeTc* tc, const VaeDev& P, const WinSrc& src, const VaeIO& io,
     TcDev T;
     memset(&T, 0, sizeof(T));
     T.n_pass = 2 * L; T.L = L;
-    T.scratch = static_cast<unsigned char*>(tc->scratch); T.scratch_stride = stride;
+    T.scratch = static_cast<unsigned char*>(tc->scratch); T.scratch_stride = stride; T.g_bytes = g_bytes;
     T.dbg = tc->dbg;
     for (int p = 0; p < 2 * L; ++p) {
         const bool dec = p >= L;
         const int l = dec ? p - L : p;
         T.pass[p].w = static_cast<const unsigned char*>(tc->wpack) + tc->pass_off[p];
         T.pass[p].bias = tc->bias + (size_t)p * 4 * H;
-        T.pass[p].in_kind = (l > 0) ? IN_STREAM : (dec ? IN_CONST : IN_X);
+        T.pass[p].in_kind = (l > 0) ? IN_STREAM : (dec ? (hoist ? IN_HOIST : IN_CONST) : IN_X);
         T.pass[p].sink = (l < L - 1) ? SINK_STREAM : (dec ? SINK_LAST_DEC : SINK_LAST_ENC);
     }
     if (H == 128) vae_score_tc_kernel<128><<<grid, TC_THREADS, TcSmem<128>::total, st>>>(P, T, src, io);
