@@ -273,8 +273,26 @@ extern "C" int shm_vae_score(shm_vae* h, const shm_window_src* src_host, const i
     if (n == 0) return SHM_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     VaeIO io;
-    io.idx = idx; io.n_dev = n_dev; io.eps = eps; io.n = n; io.z_in = nullptr;
+    memset(&io, 0, sizeof(io));
+    io.idx = idx; io.n_dev = n_dev; io.eps = eps; io.n = n;
     io.score = score; io.mu = mu; io.logvar = logvar; io.recon = recon; io.cnn_in = cnn_in;
 
     return vae_launch(h, src, io, st);
+}
+
+extern "C" int shm_vae_rescore(shm_vae* h, const shm_window_src* src_host, const int32_t* idx, const int32_t* n_dev, const float* mu_all,
+                               const float* logvar_all, const float* eps, int64_t n, float* score, float* recon, float* cnn_in,
+                               void* stream) {
+    if (!h || !src_host || n < 0 || !mu_all || !logvar_all) return SHM_ERR_ARG;
+    if (h->engine != SHM_ENGINE_TC_BF16X3 || !vae_tc_can_rescore(&h->tc)) return SHM_ERR_UNSUPPORTED;
+    WinSrc src;
+    int rc = make_winsrc(src_host, &src);
+    if (rc != SHM_OK) return rc;
+    if (src.D != h->cfg.D) return SHM_ERR_ARG;
+    if (n == 0) return SHM_OK;
+    VaeIO io;
+    memset(&io, 0, sizeof(io));
+    io.idx = idx; io.n_dev = n_dev; io.eps = eps; io.n = n; io.mu_in = mu_all; io.logvar_in = logvar_all;
+    io.score = score; io.recon = recon; io.cnn_in = cnn_in;
+    return vae_tc_score(&h->tc, h->dev, src, io, static_cast<cudaStream_t>(stream));
 }

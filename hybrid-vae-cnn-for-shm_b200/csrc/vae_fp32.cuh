@@ -38,6 +38,8 @@ struct VaeDev {
 struct VaeIO {
     const int* idx; const int* n_dev; const float* eps;
     const float* z_in;          // decode-only entry (TemporalVAE.decode): latent supplied, encoder skipped
+    const float* mu_in;         // re-score entry: mu / logvar of an earlier pass, [all windows, Z], indexed like the windows (idx);
+    const float* logvar_in;     //   the (deterministic) encoder is skipped, z = mu + eps * exp(0.5 logvar) with this call's eps
     long long n;
     float *score, *mu, *logvar, *recon, *cnn_in;
 };

@@ -712,6 +712,20 @@ __device__ __forceinline__ void heads_stage(const PassCtx& pc, const VaeDev& P, 
     // multicasting the next pass's first stages into it
     float* muS = pc.heads_scratch;
     float* zS = muS + 2 * VAE_MAX_Z * TCM;                                    // [Z][128]
+    if (io.mu_in) {
+        // re-score: the encoder ran in an earlier call; fetch its mu / logvar for this tile's windows
+        for (int item = tid; item < 2 * P.Z * TCM; item += TC_EPI_THREADS) {
+            const int o = item / TCM, w = item - o * TCM;
+            const bool is_lv = o >= P.Z;
+            const int zi = is_lv ? o - P.Z : o;
+            float y = 0.f;
+            if (w < nvalid) {
+                const long long win = io.idx ? (long long)io.idx[n0 + w] : n0 + w;
+                y = __ldg((is_lv ? io.logvar_in : io.mu_in) + win * P.Z + zi);
+            }
+            muS[o * TCM + w] = y;
+        }
+    } else {
     if (P.has_ln) {
         if (tid < TCM) {
             float m = 0.f;
@@ -738,6 +752,7 @@ __device__ __forceinline__ void heads_stage(const PassCtx& pc, const VaeDev& P, 
             float* dst = is_lv ? io.logvar : io.mu;
             if (dst) dst[(n0 + w) * P.Z + zi] = y;
         }
+    }
     }
     epi_bar_sync();
     for (int item = tid; item < P.Z * TCM; item += TC_EPI_THREADS) {
@@ -866,6 +881,7 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
         if (sink == SINK_LAST_DEC) xhat_base += (uint32_t)T;
     };
     const bool encode_only_call = !io.score && !io.recon && !io.cnn_in;
+    const int p_first = io.mu_in ? TC.L : 0;       // re-score: mu / logvar are given, the encoder passes are skipped
 
     // Role groups at top level so that each group's code is dominated by its setmaxnreg: the two epilogue
     // warpgroups take 208 registers per thread (cell state + accumulator slices + deep ILP), the
@@ -877,7 +893,7 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
             pc.n0 = tile < n_tiles ? (long long)tile * TCM : 0;
             pc.nvalid = tile < n_tiles ? (int)min((long long)TCM, n_eff - pc.n0) : 0;
             pc.hT_buf = 1;                         // in-buffer that receives the encoder's fp32 h_T
-            for (int p = 0; p < TC.n_pass; ++p) {
+            for (int p = p_first; p < TC.n_pass; ++p) {
                 int in_kind, sink;
                 pass_setup(p, in_kind, sink);
                 if (p == TC.L) heads_stage<H>(pc, P, io);
@@ -907,7 +923,7 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
             pc.n0 = tile < n_tiles ? (long long)tile * TCM : 0;
             pc.nvalid = tile < n_tiles ? (int)min((long long)TCM, n_eff - pc.n0) : 0;
             pc.hT_buf = 1;
-            for (int p = 0; p < TC.n_pass; ++p) {
+            for (int p = p_first; p < TC.n_pass; ++p) {
                 int in_kind, sink;
                 pass_setup(p, in_kind, sink);
                 cta_sync();                        // (A)
@@ -1074,6 +1090,8 @@ void vae_tc_free(VaeTc* tc) {
     tc->dbg = nullptr;
     tc->wpack = nullptr; tc->bias = nullptr; tc->scratch = nullptr;
 }
+
+bool vae_tc_can_rescore(const VaeTc* tc) { return tc->H == 128 || tc->L > 1; }
 
 int vae_tc_score(VaeTc* tc, const VaeDev& P, const WinSrc& src, const VaeIO& io, cudaStream_t st) {
     int dev = 0;

@@ -25,5 +25,6 @@ int vae_tc_alloc(VaeTc* tc, const shm_vae_cfg& cfg);
 int vae_tc_pack(VaeTc* tc, const shm_vae_cfg& cfg, const VaeTcRaw& raw, cudaStream_t st);
 void vae_tc_free(VaeTc* tc);
 int vae_tc_score(VaeTc* tc, const VaeDev& P, const WinSrc& src, const VaeIO& io, cudaStream_t st);
+bool vae_tc_can_rescore(const VaeTc* tc);      // io.mu_in / io.logvar_in (encoder skipped) is implemented by the single-tile kernels only
 
 }  // namespace shm

@@ -74,6 +74,7 @@ SIGNATURES = {
     "shm_vae_engine": (C.c_int, [_vp]),
     "shm_vae_debug_counters": (C.c_int, [_vp, _vp, C.c_int]),
     "shm_vae_score": (C.c_int, [_vp, C.POINTER(WindowSrc), _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "shm_vae_rescore": (C.c_int, [_vp, C.POINTER(WindowSrc), _vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "shm_vae_decode": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, _vp]),
     "shm_vae_param_count": (C.c_int64, [C.POINTER(VaeCfg)]),
     "shm_vae_trainer_create": (C.c_int, [C.POINTER(_vp), C.POINTER(VaeCfg), C.c_int32, C.c_int32, C.c_int]),

@@ -202,6 +202,52 @@ class VaeScorer:
                                           _ptr(mu), _ptr(lv), _ptr(recon), _ptr(cnn_in), _stream()), "shm_vae_score")
         return out
 
+    def rescore(self, src: WindowSource, mu_all: torch.Tensor, logvar_all: torch.Tensor, eps: Optional[torch.Tensor],
+                idx: Optional[torch.Tensor] = None, n: Optional[int] = None, n_dev: Optional[torch.Tensor] = None,
+                want_score: bool = False, want_recon: bool = False, want_cnn_in: bool = True, out: Optional[dict] = None):
+        """Second pass on (flagged) windows with fresh noise, reusing the first pass's encoder outputs `mu_all` / `logvar_all`
+        ([all windows, Z], from score(..., want_latent=True)): the deterministic encoder is skipped (shm_vae_rescore).
+        Returns None when the engine has no re-score path (call score instead)."""
+        if src.D != self.D:
+            raise ShmfastError(f"window source has D={src.D}, model expects {self.D}")
+        mu_all, logvar_all = _f32c(mu_all, "mu_all"), _f32c(logvar_all, "logvar_all")
+        if mu_all.shape != logvar_all.shape or mu_all.dim() != 2 or mu_all.shape[1] != self.Z or mu_all.shape[0] < src.n_windows:
+            raise ShmfastError("mu_all / logvar_all must be [n_windows, Z]")
+        if idx is not None:
+            _need_cuda(idx, "idx")
+            if idx.dtype != torch.int32:
+                raise ShmfastError("idx must be int32")
+            n = idx.numel() if n is None else n
+        n = src.n_windows if n is None else int(n)
+        dev = src.data.device
+        if eps is not None:
+            eps = _f32c(eps, "eps")
+            if eps.numel() < n * self.Z:
+                raise ShmfastError("eps must hold [n, Z] values")
+        out = {} if out is None else out
+
+        def buf(name, want, shape):
+            if not want:
+                return None
+            t = out.get(name)
+            if t is None:
+                t = torch.empty(shape, dtype=torch.float32, device=dev)
+                out[name] = t
+            return t
+
+        score = buf("score", want_score, (n,))
+        recon = buf("recon", want_recon, (n, src.T, self.D))
+        cnn_in = buf("cnn_in", want_cnn_in, (n, 2, src.T, self.D))
+        if n == 0:
+            return out
+        with torch.cuda.device(dev):
+            rc = self._lib.shm_vae_rescore(self._h, C.byref(src.struct), _ptr(idx), _ptr(n_dev), _ptr(mu_all), _ptr(logvar_all), _ptr(eps),
+                                           n, _ptr(score), _ptr(recon), _ptr(cnn_in), _stream())
+        if rc == -2:                                  # SHM_ERR_UNSUPPORTED: this engine / model has no re-score path
+            return None
+        check(rc, "shm_vae_rescore")
+        return out
+
     def debug_counters(self, n_cta: int = 148):
         """Tensor-core engine profiling counters [n_cta, 8] (first call enables them)."""
         buf = np.zeros((n_cta, 3, 8), dtype=np.int64)     # roles: MMA issuer, window-staging warp, epilogue warp 0

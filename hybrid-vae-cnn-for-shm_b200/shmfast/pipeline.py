@@ -41,7 +41,7 @@ class Hybrid4dof:
         windows with fresh noise (eps2[j] belongs to the j-th flagged window, the order in which the
         reference draws them) -> residual stack -> CNN -> label = argmax+1, p_struct."""
         n = src.n_windows if n is None else int(n)
-        out = self.vae.score(src, eps1, n=n)
+        out = self.vae.score(src, eps1, n=n, want_latent=True)     # mu / logvar feed the second pass (the encoder is deterministic)
         score = out["score"]
         flag, idx, count = ops.compact(score, self.thr)
         if sync_count:
@@ -54,7 +54,9 @@ class Hybrid4dof:
             res.update(logits=torch.empty((0, 2), device=dev), label=torch.empty((0,), dtype=torch.int64, device=dev),
                        p_struct=torch.empty((0,), device=dev))
             return res
-        second = self.vae.score(src, eps2, n=n_f, idx=idx, n_dev=count, want_score=False, want_cnn_in=True)
+        second = self.vae.rescore(src, out["mu"], out["logvar"], eps2, idx=idx, n=n_f, n_dev=count, want_cnn_in=True)
+        if second is None:                                         # engine without a re-score path: full forward, same result
+            second = self.vae.score(src, eps2, n=n_f, idx=idx, n_dev=count, want_score=False, want_cnn_in=True)
         logits, label, p_struct = self.cnn.forward(second["cnn_in"], n=n_f, n_dev=count, want_labels=True)
         res.update(logits=logits, label=label, p_struct=p_struct, cnn_in=second["cnn_in"])
         return res

@@ -152,6 +152,15 @@ int shm_vae_score(shm_vae* h, const shm_window_src* src_host, const int32_t* idx
                   const float* eps, int64_t n, float* score, float* mu, float* logvar, float* recon,
                   float* cnn_in, void* stream);
 
+/* Second pass of the hybrid loop on the flagged windows (06_test_full_pipeline.py:360-365: `recon, _, _ = vae(z_sel)` with fresh noise;
+ * training-time twin 05_train_cnn.py:118-141).  In eval mode the encoder is deterministic, so its outputs of the first pass are reused:
+ * mu_all / logvar_all [N_all, Z] are shm_vae_score's mu / logvar over ALL windows of `src`; entry j works on window idx[j] (or j if idx
+ * is NULL), z = mu_all[idx[j]] + eps[j] * exp(0.5 * logvar_all[idx[j]]), then decode + residual exactly as shm_vae_score does.  Results are
+ * bit-identical to shm_vae_score(src, idx, ..., eps) on the same engine.  SHM_ERR_UNSUPPORTED unless the handle runs the tensor-core
+ * engine on a stacked (L >= 2) or H = 128 model: call shm_vae_score instead. */
+int shm_vae_rescore(shm_vae* h, const shm_window_src* src_host, const int32_t* idx, const int32_t* n_dev, const float* mu_all,
+                    const float* logvar_all, const float* eps, int64_t n, float* score, float* recon, float* cnn_in, void* stream);
+
 /* TemporalVAE.decode(z, seq_len) (temporal_vae.py:65-70): z [n,Z] -> recon [n,T,D]. */
 int shm_vae_decode(shm_vae* h, const float* z, int64_t n, int32_t T, float* recon, void* stream);
 
