@@ -5,14 +5,15 @@
 // Single pass, HBM-bound (4 B read, 1 B flag + 4 B per flagged window written): tiles are claimed in
 // order through an atomic ticket, each CTA ballots its flags, publishes its tile aggregate and
 // resolves its exclusive prefix with a warp-wide decoupled look-back, so the scores are read exactly
-// once and the output order equals np.where's.
+// once and the output order equals np.where's.  The tile's indices are staged in shared memory while
+// the look-back runs and leave as coalesced stores.
 #include "common.cuh"
 
 namespace shm {
 
-constexpr int CP_THREADS = 1024;
-constexpr int CP_ITEMS = 32;          // 32768 scores (128 KB) per tile: one fat CTA per SM keeps the look-back window short
-                                      // (~#SM tiles in flight) and 128 KB of loads in flight per SM
+constexpr int CP_THREADS = 512;
+constexpr int CP_ITEMS = 32;          // 16384 scores (64 KB) per tile, 4 tiles per SM: 128 KB of loads in flight per SM in each of the two
+                                      // load batches, and one tile's look-back / write-out phase runs under the other tiles' load phase
 constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
 
 constexpr unsigned long long ST_AGG = 1ull << 62;
@@ -27,33 +28,39 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(CP_THREADS)
+__global__ void __launch_bounds__(CP_THREADS, 4)
 compact_kernel(const float* __restrict__ score, float thr, long long N, unsigned char* __restrict__ flag,
                int* __restrict__ idx, int* __restrict__ count, int* ticket, unsigned long long* status, int n_tiles,
                int vec_ok) {
     __shared__ int s_tile;
     __shared__ int s_warp[CP_THREADS / 32];
     __shared__ int s_excl;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1);
-    __syncthreads();
-    const int tile = s_tile;
-    if (tile >= n_tiles) return;
-    const long long base = (long long)tile * CP_TILE + (long long)tid * CP_ITEMS;
-
     __shared__ __align__(16) unsigned char s_nib[CP_TILE / 4];
+    __shared__ unsigned short s_idx[CP_TILE];                       // the tile's flagged offsets, in order: written out coalesced
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // tile = blockIdx.x: CTAs are dispatched in index order, so every predecessor a look-back waits for is resident or done
+    // (the forward-progress assumption of every single-pass decoupled look-back scan); a ticket counter would serialise
+    // one same-address atomic per tile
+    const int tile = blockIdx.x;
+    (void)ticket; (void)s_tile;
     const long long tile_base = (long long)tile * CP_TILE;
+    const long long base = tile_base + (long long)tid * CP_ITEMS;
     const bool full = vec_ok && tile_base + CP_TILE <= N;
     unsigned bits = 0;
     if (full) {
         // coalesced 16-byte loads (consecutive lanes -> consecutive float4s), flags parked as nibbles in shared memory,
-        // then every thread picks up the 32 consecutive scores it owns for the scan
+        // then every thread picks up the 16 consecutive scores it owns for the scan
         const float4* s4 = reinterpret_cast<const float4*>(score + tile_base);
 #pragma unroll
-        for (int q = 0; q < CP_ITEMS / 4; ++q) {
-            const float4 a = __ldcs(s4 + q * CP_THREADS + tid);
-            s_nib[q * CP_THREADS + tid] = (unsigned char)((a.x > thr ? 1u : 0u) | (a.y > thr ? 2u : 0u) | (a.z > thr ? 4u : 0u) |
-                                                          (a.w > thr ? 8u : 0u));          // NaN > thr is false, as NumPy
+        for (int h = 0; h < 2; ++h) {                                   // two batches of 4 loads: 32 registers per thread at 4 CTAs per SM
+            float4 a[CP_ITEMS / 8];
+#pragma unroll
+            for (int q = 0; q < CP_ITEMS / 8; ++q) a[q] = __ldcs(s4 + (h * (CP_ITEMS / 8) + q) * CP_THREADS + tid);
+#pragma unroll
+            for (int q = 0; q < CP_ITEMS / 8; ++q)
+                s_nib[(h * (CP_ITEMS / 8) + q) * CP_THREADS + tid] =
+                    (unsigned char)((a[q].x > thr ? 1u : 0u) | (a[q].y > thr ? 2u : 0u) | (a[q].z > thr ? 4u : 0u) |
+                                    (a[q].w > thr ? 8u : 0u));                              // NaN > thr is false, as NumPy
         }
         __syncthreads();
         const unsigned long long nb = *reinterpret_cast<const unsigned long long*>(s_nib + tid * (CP_ITEMS / 4));
@@ -98,10 +105,22 @@ compact_kernel(const float* __restrict__ score, float thr, long long N, unsigned
         if (w < warp) warp_off += c;
         agg += c;
     }
+    // publish the aggregate first, then stage this tile's indices while the predecessors resolve
+    if (tid == 0) st_status(status + tile, (tile == 0 ? ST_INC : ST_AGG) | (unsigned)agg);
+    {
+        int loc = warp_off + (incl - cnt);
+        unsigned b = bits;
+        while (b) {
+            const int i = __ffs(b) - 1;
+            b &= b - 1;
+            s_idx[loc++] = (unsigned short)(tid * CP_ITEMS + i);
+        }
+    }
 
-    // decoupled look-back (warp 0)
+    // decoupled look-back (warp 0): 32 predecessors per round.  (A 512-wide round -- 16 statuses per lane -- was measured and is
+    // slower, 27 % instead of 53 % of the HBM roof: every spin re-reads 4 KB of statuses and the window almost always holds an
+    // unpublished tile.)
     if (warp == 0) {
-        if (lane == 0) st_status(status + tile, (tile == 0 ? ST_INC : ST_AGG) | (unsigned)agg);
         int excl = 0;
         int look = tile - 1;
         while (look >= 0) {
@@ -131,10 +150,8 @@ compact_kernel(const float* __restrict__ score, float thr, long long N, unsigned
         }
     }
     __syncthreads();
-    int pos = s_excl + warp_off + (incl - cnt);
-#pragma unroll
-    for (int i = 0; i < CP_ITEMS; ++i)
-        if ((bits >> i) & 1u) idx[pos++] = (int)(base + i);
+    const int excl = s_excl;
+    for (int j = tid; j < agg; j += CP_THREADS) idx[excl + j] = (int)(tile_base + s_idx[j]);
 }
 
 }  // namespace shm
