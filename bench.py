@@ -231,7 +231,7 @@ def run_shmfast(a):
             out = vae.score(src, eps1, n=N, want_latent=hybrid, out=step.first)
         score = out["score"]
         flag, idx, count = ops.compact(score, thr)
-        launches = 2
+        launches = 4                                                       # scorer + the three compaction kernels
         if a.workload == "4dof_hybrid":
             # second pass with fresh noise; the (deterministic) encoder's mu / logvar of the first pass are reused
             second = vae.rescore(src, out["mu"], out["logvar"], eps2, idx=idx, n=max_flag, n_dev=count, want_cnn_in=True, out=step.buf)
@@ -537,7 +537,7 @@ def run_openlab(a):
             "e2e": {"value": windows_total / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": int(pinned.numel() * 4),
                     "d2h_bytes_per_step": int(N * (4 + 1 + 8 + 8) + 4), "ms_per_step": 1e3 * e2e_s / a.steps,
                     "api": "shmfast.stream.HostStream around shmfast.pipeline.HybridOpenLab.run + scatter_flagged (copies on side streams under the next chunk's kernels)"},
-            "gpu_launches": 3 * a.steps,
+            "gpu_launches": (4 + 12 * ((n_flag + 8191) // 8192)) * a.steps,      # scorer, 3 compaction kernels, 12 CNN kernels per 8192-window chunk
             "roofline": {"bound": "tensor", "kernel": "vae_score (fused LSTM-VAE scorer)", "achieved": achieved, "peak": pk["tf_sust"],
                          "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
                          "traffic": NCU_DRAM_BYTES_PER_WINDOW_OPENLAB * N if vae.engine == ops.ENGINE_TC_BF16X3 else None,
@@ -688,7 +688,7 @@ def run_train(a):
             "clocks": clocks, "phases": phases,
             "e2e": {"value": windows_total / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": B * T * D * 4, "d2h_bytes_per_step": 12,
                     "ms_per_step": 1e3 * e2e_s / a.steps, "api": "shmfast.train.VaeTrainer.step (pinned host batch in, loss out)"},
-            "gpu_launches": None,
+            "gpu_launches": 47 * a.steps,        # profiles/r01_train_launches_v2.csv: 141 libshmfast launches in 3 steps (21 contractions, 8 recurrence, ...)
             "roofline": {"bound": "fp32", "kernel": "whole step (fp32 FMA contractions + resident-weight recurrence)", "achieved": achieved,
                          "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
                          "peak_source": "derived: 148 SM x 128 FMA lanes x 2 x 1.965 GHz", "algorithmic_flop_per_window": TRAIN_FLOP_PER_WINDOW},
