@@ -90,11 +90,17 @@ window_tile_kernel(WinSrc src, const int* __restrict__ idx, long long N, float* 
         }
         __syncthreads();
         if (vec) {
-            const int c4 = TD >> 2;
-            for (int w = warp; w < nw; w += WT_THREADS / 32) {
-                const float4* s4 = reinterpret_cast<const float4*>(tile + w * slab);
-                float4* o4 = reinterpret_cast<float4*>(out + (n0 + w) * TD);
-                for (int c = lane; c < c4; c += 32) __stcs(o4 + c, s4[c]);
+            // the group's windows are one contiguous run of the output: walk it with all threads (no idle lanes on the last
+            // 16-byte chunk of a window), stepping (window, chunk) incrementally instead of dividing
+            const int c4 = TD >> 2, slab4 = slab >> 2;
+            const float4* s4 = reinterpret_cast<const float4*>(tile);
+            float4* o4 = reinterpret_cast<float4*>(out + n0 * TD);
+            const int dq = WT_THREADS / c4, dr = WT_THREADS - dq * c4;
+            int w = tid / c4, c = tid - w * c4;
+            for (int i = tid; i < nw * c4; i += WT_THREADS) {
+                __stcs(o4 + i, s4[w * slab4 + c]);
+                w += dq; c += dr;
+                if (c >= c4) { c -= c4; ++w; }
             }
         } else {
             for (int w = warp; w < nw; w += WT_THREADS / 32)
@@ -128,7 +134,7 @@ extern "C" int shm_window_normalize(const shm_window_src* src_host, const int32_
         if (idx == nullptr) {                                       // consecutive windows share the staged rows
             const int max_rows = WT_SMEM_FLOATS / w.D;
             group = (max_rows - w.T) / step_rows + 1;
-            group = group > 64 ? 64 : group;
+            group = group > 128 ? 128 : group;
         } else {                                                    // gathered windows: one slab each
             group = WT_SMEM_FLOATS / TD;
             group = group > 16 ? 16 : group;
