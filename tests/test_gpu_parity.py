@@ -364,3 +364,32 @@ def test_full_size_properties(cuda_dev):
     flag, idx, count = ops.compact(a, float(np.percentile(a.cpu().numpy(), 99.0)))
     kk = int(count.item())
     assert abs(kk - 0.01 * N) <= 2 and bool((idx[1:kk] > idx[:kk - 1]).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [(1 << 17) + 128 * 3 + 5, 129, 1])
+def test_full_size_properties_openlab(cuda_dev, N):
+    """The two-tile H=64 scorer (vae_tc_dual.cuh) at stream size and at the pairing edge cases (odd number of tiles, a lone
+    ragged tile, one window): deterministic, and a window's score does not depend on the tile / pair it lands in -- a random
+    subset re-scored through a gather list, and as materialised windows, agrees bit for bit; a handful against the oracle."""
+    s = synth.STAGES["openlab"]
+    sd = synth.stage_vae_weights("openlab", seed=0)
+    rows = (N - 1) * s["stride"] + s["T"]
+    series = to_dev(synth.series(rows, s["D"], seed=3), cuda_dev)
+    eps = to_dev(synth.eps(N, s["Z"], seed=3), cuda_dev)
+    vae = ops.VaeScorer(sd, cuda_dev)
+    src = ops.WindowSource(series, s["T"], stride=s["stride"])
+    a = vae.score(src, eps)["score"]
+    assert torch.equal(a, vae.score(src, eps)["score"]) and torch.isfinite(a).all()
+    m = min(N, 1000)
+    sel = torch.randperm(N, device=cuda_dev)[:m].to(torch.int32)
+    e_sel = eps[sel.long()].contiguous()
+    b = vae.score(src, e_sel, idx=sel)["score"]                # same windows, different tiles and pair partners
+    assert torch.equal(b, a[sel.long()])
+    Wm = ops.window_normalize(src, idx=sel)
+    c = vae.score(ops.WindowSource(Wm, s["T"]), e_sel)["score"]
+    assert torch.equal(c, a[sel.long()])
+    k = min(m, 8)
+    Wk = Wm[:k].cpu().numpy()
+    ro, _, _ = O.vae_forward(sd, Wk, e_sel[:k].cpu().numpy(), np.float64)
+    assert rel_err(a[sel[:k].long()].cpu().numpy(), O.mse_score(Wk.astype(np.float64), ro)) < REL_TOL
