@@ -75,3 +75,22 @@ def test_stream_rejects_unpinned_and_oversized(cuda_dev):
         list(pipe.run(iter([torch.zeros((65, 4)).pin_memory()]), lambda sd, i: dict(x=sd[:64, 0])))
     with pytest.raises(ops.ShmfastError):
         HostStream(torch.device("cpu"), (4, 4), {})
+
+
+def test_async_hybrid_with_nothing_flagged(cuda_dev):
+    """sync_count=False sizes the second pass by capacity and lets the kernels read the flagged count on the device: a chunk
+    with no flagged window (count = 0) must run through rescore / CNN / scatter as a no-op."""
+    T, D, Z, N = 100, 12, 16, 300
+    vae = ops.VaeScorer(synth.stage_vae_weights("4dof", seed=2), cuda_dev)
+    cnn = ops.Cnn4dof(synth.cnn4dof_weights(seed=2), cuda_dev)
+    mean, std = synth.stats(D, seed=2)
+    series = torch.from_numpy(synth.series(N + T - 1, D, seed=2)).to(cuda_dev)
+    src = ops.WindowSource(series, T, stride=1, mean=mean, std=guard_std_4dof(std), nan_to_zero=True)
+    eps1 = torch.randn((N, Z), device=cuda_dev)
+    eps2 = torch.randn((N, Z), device=cuda_dev)
+    res = Hybrid4dof(vae, cnn, float("inf")).run(src, eps1, eps2, sync_count=False, max_flagged=128)
+    y, p = scatter_flagged(res["idx"], res["count"], N, [res["label"], res["p_struct"]], [torch.int64, torch.float32])
+    torch.cuda.synchronize()
+    assert int(res["count"].item()) == 0 and int(res["flag"].sum()) == 0
+    assert int(y.abs().sum()) == 0 and float(p.abs().sum()) == 0.0
+    assert torch.equal(res["score"], vae.score(src, eps1)["score"])
