@@ -81,7 +81,8 @@ compact_flag_kernel(const float* __restrict__ score, float thr, long long N, uns
     }
 }
 
-// exclusive scan of the tile counts (one CTA, 1024 tiles per round with a running carry) and the total
+// exclusive scan of the tile counts (one CTA, 8 consecutive tiles per thread = 8192 tiles per round, running carry) and the total
+constexpr int CS_ITEMS = 8;
 __global__ void __launch_bounds__(1024)
 compact_scan_kernel(const int* __restrict__ tile_count, int n_tiles, int* __restrict__ tile_off, int* __restrict__ count) {
     __shared__ int s_warp[32];
@@ -89,10 +90,16 @@ compact_scan_kernel(const int* __restrict__ tile_count, int n_tiles, int* __rest
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (int b0 = 0; b0 < n_tiles; b0 += 1024) {
-        const int t = b0 + tid;
-        const int v = t < n_tiles ? tile_count[t] : 0;
-        int incl = v;
+    for (int b0 = 0; b0 < n_tiles; b0 += 1024 * CS_ITEMS) {
+        const int t0 = b0 + tid * CS_ITEMS;
+        int v[CS_ITEMS];
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < CS_ITEMS; ++k) {
+            v[k] = (t0 + k < n_tiles) ? tile_count[t0 + k] : 0;
+            sum += v[k];
+        }
+        int incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int y = __shfl_up_sync(0xffffffffu, incl, o);
@@ -111,8 +118,12 @@ compact_scan_kernel(const int* __restrict__ tile_count, int n_tiles, int* __rest
         }
         __syncthreads();
         const int carry = s_carry;
-        const int excl = carry + (warp ? s_warp[warp - 1] : 0) + incl - v;
-        if (t < n_tiles) tile_off[t] = excl;
+        int excl = carry + (warp ? s_warp[warp - 1] : 0) + incl - sum;
+#pragma unroll
+        for (int k = 0; k < CS_ITEMS; ++k) {
+            if (t0 + k < n_tiles) tile_off[t0 + k] = excl;
+            excl += v[k];
+        }
         __syncthreads();
         if (tid == 1023) s_carry = carry + s_warp[31];
         __syncthreads();
@@ -126,10 +137,11 @@ compact_write_kernel(const unsigned* __restrict__ mask, const int* __restrict__ 
     __shared__ int s_warp[CP_THREADS / 32];
     __shared__ unsigned short s_idx[CP_TILE];                       // the tile's flagged offsets, in order: written out coalesced
     const int tile = blockIdx.x;
-    const int agg = tile_count[tile];
-    if (agg == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int agg = tile_count[tile];                               // the three loads are independent: one round trip
+    const int excl = tile_off[tile];
     unsigned b = mask[(long long)tile * CP_THREADS + tid];
+    if (agg == 0) return;
     const int cnt = __popc(b);
     int incl = cnt;
 #pragma unroll
@@ -149,7 +161,6 @@ compact_write_kernel(const unsigned* __restrict__ mask, const int* __restrict__ 
     }
     __syncthreads();
     const long long tile_base = (long long)tile * CP_TILE;
-    const int excl = tile_off[tile];
     for (int j = tid; j < agg; j += CP_THREADS) idx[excl + j] = (int)(tile_base + s_idx[j]);
 }
 
