@@ -14,13 +14,19 @@
 //   * the layer input (x_t, the lower layer's h_t stream, or the constant decoder input u) is an
 //     A operand in shared memory (K-major, no-swizzle core-matrix image).
 //   * weights (pre-scaled by -log2(e) / -2log2(e) so the accumulator is directly the ex2 argument)
-//     stream L2 -> smem through a 4-stage ring of 1-D bulk async copies (TMA engine) gated by mbarriers.
-//   * warp-specialised persistent CTA (one per SM): 8 epilogue warps (LSTM cell in registers,
-//     ex2/rcp with merged divisions: 7 MUFU per cell), 1 copy-producer warp, 1 MMA-issuer warp,
-//     1 window-staging warp.  Two 128-column accumulator buffers let chunk c+1's MMAs overlap chunk c's
+//     stream L2 -> smem through a 5-stage ring of 1-D bulk async copies (TMA engine) gated by mbarriers;
+//     the two CTAs of a cluster walk the same stream in lock step, each loads half of every stage and
+//     multicasts it into both rings (TC_CLUSTER).
+//   * warp-specialised persistent CTA (one per SM): 16 epilogue warps (LSTM cell in registers,
+//     ex2/rcp with merged divisions: 7 MUFU per cell), 4 window-staging / output warps, 1 copy-producer
+//     warp, 1 MMA-issuer warp.  Two 128-column accumulator buffers let chunk c+1's MMAs overlap chunk c's
 //     cell update; the input-projection MMAs of step t+1 overlap the tail of step t.
 //   * layers of a stack run one after the other over all T steps; the lower layer's h_t stream goes
 //     through a per-CTA global scratch (written once, read once by bulk copies).
+//   * the decoder's first layer sees the same input at every step: its input projection is computed once
+//     per tile and added by the cell update instead of the bias (IN_HOIST); a re-score call (io.mu_in)
+//     starts at the heads stage with the encoder outputs of an earlier call.
+//   * the single-layer H = 64 model runs two tiles per CTA with resident weights: vae_tc_dual.cuh.
 #include "tcgen05.cuh"
 #include "vae_tc.cuh"
 
