@@ -9,7 +9,7 @@ torch.distributed (NCCL on GPUs, gloo in the CPU tests) is used only to collect 
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist

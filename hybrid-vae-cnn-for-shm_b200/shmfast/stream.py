@@ -13,7 +13,7 @@ host synchronisation inside a chunk).
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Iterable, Optional, Sequence, Tuple
+from typing import Callable, Dict, Iterable, Sequence, Tuple
 
 import torch
 
