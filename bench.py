@@ -45,7 +45,7 @@ FLOP_PER_WINDOW = {"4dof": 80_322_560, "openlab": 13_527_040, "1dof": 4_248_512}
 CNN_FLOP_PER_FLAGGED = {"4dof": 4_070_912, "openlab": 133_851_648}
 # ncu --set full capture of vae_score_tc_kernel<128> (profiles/r01_vae_tc_raw.csv): 15.577 GB read + 15.581 GB written
 # for a 151,552-window launch
-NCU_DRAM_BYTES_PER_WINDOW_4DOF = (15.577271e9 + 15.580796e9) / 151552
+NCU_DRAM_BYTES_PER_WINDOW_4DOF = (16.249489e9 + 15.895659e9) / 151552         # profiles/r01_vae_tc_v5_raw.csv (final kernel of round 1)
 NCU_DRAM_BYTES_PER_WINDOW_OPENLAB = (41.604608e6 + 0.883456e6) / 151552      # profiles/r01_vae_tc_dual_raw.csv (algorithmic: 240 + 32 + 4)
 
 
