@@ -754,9 +754,11 @@ extern "C" int shm_vae_trainer_create(shm_vae_trainer** out, const shm_vae_cfg* 
     const int D = cfg->D, H = cfg->H, Z = cfg->Z, L = cfg->L;
     if (D < 1 || Z < 1 || L < 1 || T < 1 || max_batch < 1) return SHM_ERR_ARG;
     if (!(H == 32 || H == 64 || H == 128) || L > SHM_MAX_L || D > SHM_MAX_D || Z > 16) return SHM_ERR_UNSUPPORTED;
+    int prev = 0;
+    SHM_CUDA(cudaGetDevice(&prev));
     SHM_CUDA(cudaSetDevice(device));
     shm_vae_trainer* h = new (std::nothrow) shm_vae_trainer();
-    if (!h) return SHM_ERR_NOMEM;
+    if (!h) { cudaSetDevice(prev); return SHM_ERR_NOMEM; }
     h->cfg = *cfg; h->T = T; h->Bmax = max_batch; h->device = device; h->nsm = device_sm_count(device);
     h->pl = param_layout(*cfg);
     h->have_fwd = 0; h->B = 0; h->use_mask = 0; h->scale = 1.f;
@@ -777,20 +779,24 @@ extern "C" int shm_vae_trainer_create(shm_vae_trainer** out, const shm_vae_cfg* 
     h->dpre = take(B * H); h->dmu_t = take(B * Z); h->dlv_t = take(B * Z); h->dy = take(B * H); h->dhn = take(B * H);
     h->ws_floats = o;
     h->ws = nullptr; h->masks = nullptr;
-    if (cudaMalloc(&h->ws, o * sizeof(float)) != cudaSuccess) { cudaGetLastError(); delete h; return SHM_ERR_NOMEM; }
+    if (cudaMalloc(&h->ws, o * sizeof(float)) != cudaSuccess) { cudaGetLastError(); delete h; cudaSetDevice(prev); return SHM_ERR_NOMEM; }
     if (L > 1 && cudaMalloc(&h->masks, (size_t)2 * (L - 1) * TB * H) != cudaSuccess) {
-        cudaGetLastError(); cudaFree(h->ws); delete h; return SHM_ERR_NOMEM;
+        cudaGetLastError(); cudaFree(h->ws); delete h; cudaSetDevice(prev); return SHM_ERR_NOMEM;
     }
+    cudaSetDevice(prev);
     *out = h;
     return SHM_OK;
 }
 
 extern "C" int shm_vae_trainer_destroy(shm_vae_trainer* h) {
     if (!h) return SHM_OK;
+    int prev = 0;
+    const bool have_prev = cudaGetDevice(&prev) == cudaSuccess;
     cudaSetDevice(h->device);
     cudaFree(h->ws);
     if (h->masks) cudaFree(h->masks);
     delete h;
+    if (have_prev) cudaSetDevice(prev);
     return SHM_OK;
 }
 

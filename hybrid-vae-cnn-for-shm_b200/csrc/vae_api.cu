@@ -127,7 +127,7 @@ extern "C" int shm_vae_create(shm_vae** out, const shm_vae_cfg* cfg, const shm_v
     SHM_CUDA(cudaGetDevice(&prev));
     SHM_CUDA(cudaSetDevice(device));
     shm_vae* h = new (std::nothrow) shm_vae();
-    if (!h) return SHM_ERR_NOMEM;
+    if (!h) { cudaSetDevice(prev); return SHM_ERR_NOMEM; }
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg; h->device = device; h->engine = engine;
     if (h->cfg.ln_eps <= 0.f) h->cfg.ln_eps = 1e-5f;
@@ -216,6 +216,13 @@ extern "C" int shm_vae_destroy(shm_vae* h) {
 }
 
 extern "C" int shm_vae_engine(const shm_vae* h) { return h ? h->engine : SHM_ERR_ARG; }
+
+extern "C" int shm_vae_get_cfg(const shm_vae* h, shm_vae_cfg* out) {
+    if (!h || !out) return SHM_ERR_ARG;
+    *out = h->cfg;
+    out->engine = h->engine;
+    return SHM_OK;
+}
 
 extern "C" int shm_vae_debug_counters(shm_vae* h, long long* out_host, int n) {
     if (!h || n < 0) return SHM_ERR_ARG;

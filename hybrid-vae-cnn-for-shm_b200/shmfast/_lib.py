@@ -72,6 +72,15 @@ SIGNATURES = {
     "shm_vae_update_weights": (C.c_int, [_vp, C.POINTER(VaeWeights), _vp]),
     "shm_vae_destroy": (C.c_int, [_vp]),
     "shm_vae_engine": (C.c_int, [_vp]),
+    "shm_vae_get_cfg": (C.c_int, [_vp, C.POINTER(VaeCfg)]),
+    "shm_hybrid4dof_workspace_bytes": (C.c_int64, [_vp, C.c_int64, C.c_int64]),
+    "shm_hybrid4dof_score": (C.c_int, [_vp, _vp, C.POINTER(WindowSrc), C.c_int64, _vp, _vp, C.c_float, C.c_int64] + [_vp] * 10 +
+                             [C.c_int64, _vp]),
+    "shm_hybridol_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
+    "shm_hybridol_score": (C.c_int, [_vp, _vp, C.POINTER(WindowSrc), C.POINTER(WindowSrc), C.c_int64, _vp, C.c_float, C.c_double,
+                                     C.c_int64] + [_vp] * 10 + [C.c_int64, _vp]),
+    "shm_scatter_flagged_4dof": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, _vp]),
+    "shm_scatter_flagged_openlab": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_double, C.c_int64, _vp, _vp, _vp, _vp]),
     "shm_vae_debug_counters": (C.c_int, [_vp, _vp, C.c_int]),
     "shm_vae_score": (C.c_int, [_vp, C.POINTER(WindowSrc), _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "shm_vae_rescore": (C.c_int, [_vp, C.POINTER(WindowSrc), _vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
@@ -109,15 +118,19 @@ _lib = None
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:
-    """dlopen the in-tree library (building it with nvcc first if it is not there)."""
+    """dlopen the in-tree library.  The library is always checked against the digest of csrc/ + shmfast.h
+    (shmfast.build writes the stamp only next to a freshly linked .so): a stale binary is rebuilt with nvcc, or
+    refused when `build_if_missing` is False -- never dlopen'ed against newer ctypes signatures."""
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        if not build_if_missing:
-            raise ShmfastError(f"{LIB_PATH} is missing: run `python -m shmfast.build` (no CPU fallback exists)")
-        from . import build as _b
-        _b.build()
+    from . import build as _b
+    if build_if_missing:
+        _b.build()                                  # no-op when the stamp matches the sources
+    elif not LIB_PATH.exists():
+        raise ShmfastError(f"{LIB_PATH} is missing: run `python -m shmfast.build` (no CPU fallback exists)")
+    elif not _b.is_fresh():
+        raise ShmfastError(f"{LIB_PATH} does not match csrc/ and include/shmfast.h: run `python -m shmfast.build`")
     lib = C.CDLL(str(LIB_PATH))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)        # AttributeError here = header/library mismatch: fail loudly

@@ -41,13 +41,22 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+STAMP = LIBDIR / "libshmfast.sha256"       # git-ignored: only ever written next to a freshly linked .so
+
+
+def is_fresh() -> bool:
+    return LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == _digest()
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     LIBDIR.mkdir(exist_ok=True)
     OBJDIR.mkdir(exist_ok=True)
-    stamp = LIBDIR / "libshmfast.sha256"
+    stamp = STAMP
     dig = _digest()
-    if not force and LIB.exists() and stamp.exists() and stamp.read_text().strip() == dig:
+    if not force and is_fresh():
         return LIB
+    if stamp.exists():
+        stamp.unlink()                           # a failed build must not leave a matching stamp behind
     cc = nvcc()
 
     def compile_one(src: Path):

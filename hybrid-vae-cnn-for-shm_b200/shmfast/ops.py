@@ -276,6 +276,19 @@ class VaeScorer:
             pass
 
 
+_WS_CACHE: dict = {}
+
+
+def _workspace(dev: torch.device, nbytes: int, tag: str) -> torch.Tensor:
+    """Per-(device, stream, purpose) scratch, grown on demand and reused: no allocation on the per-chunk path."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, tag)
+    t = _WS_CACHE.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=dev)
+        _WS_CACHE[key] = t
+    return t
+
+
 def compact(score: torch.Tensor, thr: float, want_flag: bool = True):
     """flag = score > thr (strict fp32), idx = np.where(flag)[0] ascending, count (device int32[1]).
     06_test_full_pipeline.py:350-351."""
@@ -286,7 +299,7 @@ def compact(score: torch.Tensor, thr: float, want_flag: bool = True):
     flag = torch.empty((N,), dtype=torch.uint8, device=dev) if want_flag else None
     idx = torch.empty((max(N, 1),), dtype=torch.int32, device=dev)
     count = torch.empty((1,), dtype=torch.int32, device=dev)
-    ws = torch.empty((int(lib.shm_compact_workspace_bytes(N)),), dtype=torch.uint8, device=dev)
+    ws = _workspace(dev, int(lib.shm_compact_workspace_bytes(N)), "compact")
     with torch.cuda.device(dev):
         check(lib.shm_compact(_ptr(score), float(np.float32(thr)), N, _ptr(flag), _ptr(idx), _ptr(count), _ptr(ws), _stream()),
               "shm_compact")
@@ -465,7 +478,131 @@ def percentile(scores: torch.Tensor, q: float) -> torch.Tensor:
     scores = _f32c(scores, "scores")
     dev = scores.device
     res = torch.empty((1,), dtype=torch.float64, device=dev)
-    ws = torch.empty((int(lib.shm_percentile_workspace_bytes(scores.numel())),), dtype=torch.uint8, device=dev)
+    ws = _workspace(dev, int(lib.shm_percentile_workspace_bytes(scores.numel())), "percentile")
     with torch.cuda.device(dev):
         check(lib.shm_percentile(_ptr(scores), scores.numel(), float(q), _ptr(res), _ptr(ws), _stream()), "shm_percentile")
     return res
+
+
+def scatter_flagged_4dof(idx: torch.Tensor, count: Optional[torch.Tensor], cap: int, label: torch.Tensor, p_struct: torch.Tensor,
+                         n: int):
+    """y_pred[idx[j]] = label[j]; hyb_score_full[idx[j]] = p_struct[j] for j < min(count, cap); 0 elsewhere
+    (06_test_full_pipeline.py:336,356,368-372).  One kernel + two memsets; `count` stays on the device."""
+    lib = _lib.load()
+    _need_cuda(idx, "idx")
+    dev = idx.device
+    y_pred = torch.empty((n,), dtype=torch.int64, device=dev)
+    p_full = torch.empty((n,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.shm_scatter_flagged_4dof(_ptr(idx), _ptr(count), int(cap), _ptr(label), _ptr(p_struct), int(n), _ptr(y_pred),
+                                           _ptr(p_full), _stream()), "shm_scatter_flagged_4dof")
+    return y_pred, p_full
+
+
+def scatter_flagged_openlab(idx: torch.Tensor, count: Optional[torch.Tensor], cap: int, prob: torch.Tensor, cnn_thr: float, n: int):
+    """pred_bin = prob_st >= thr (fp64, 10_test_hybrid_pipeline.py:300-301); dense y_pred (0 not flagged / 1 sensor fault /
+    2 structural, :389-401) and prob_full."""
+    lib = _lib.load()
+    _need_cuda(idx, "idx")
+    dev = idx.device
+    pred_bin = torch.empty((cap,), dtype=torch.int64, device=dev)
+    y_pred = torch.empty((n,), dtype=torch.int64, device=dev)
+    prob_full = torch.empty((n,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.shm_scatter_flagged_openlab(_ptr(idx), _ptr(count), int(cap), _ptr(prob), float(cnn_thr), int(n), _ptr(pred_bin),
+                                              _ptr(y_pred), _ptr(prob_full), _stream()), "shm_scatter_flagged_openlab")
+    return pred_bin, y_pred, prob_full
+
+
+def hybrid4dof_score(vae: VaeScorer, cnn: Cnn4dof, src: WindowSource, eps1: Optional[torch.Tensor], eps2: Optional[torch.Tensor],
+                     thr: float, n: Optional[int] = None, max_flagged: Optional[int] = None, want_flag: bool = True,
+                     want_compact: bool = True, want_dense: bool = True, out: Optional[dict] = None) -> dict:
+    """eval_group of 06_test_full_pipeline.py:327-383 as ONE C call (shm_hybrid4dof_score): no host synchronisation.
+    Returns score, flag, idx, status (device int32[2]: flagged count, overflow), logits/label/p_struct [max_flagged]
+    (want_compact) and the dense y_pred / p_full [n] (want_dense)."""
+    lib = _lib.load()
+    n = src.n_windows if n is None else int(n)
+    cap = n if max_flagged is None else min(n, int(max_flagged))
+    dev = src.data.device
+    Z = vae.Z
+    for t, name, need in ((eps1, "eps1", n * Z), (eps2, "eps2", cap * Z)):
+        if t is not None:
+            _f32c(t, name)
+            if t.numel() < need:
+                raise ShmfastError(f"{name} must hold {need} values")
+    out = {} if out is None else out
+
+    def buf(name, want, shape, dt):
+        if not want:
+            return None
+        t = out.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=dt, device=dev)
+            out[name] = t
+        return t
+
+    score = buf("score", True, (n,), torch.float32)
+    flag = buf("flag", want_flag, (n,), torch.uint8)
+    idx = buf("idx", True, (max(n, 1),), torch.int32)
+    status = buf("status", True, (2,), torch.int32)
+    logits = buf("logits", want_compact, (cap, 2), torch.float32)
+    label = buf("label", want_compact, (cap,), torch.int64)
+    p_struct = buf("p_struct", want_compact, (cap,), torch.float32)
+    y_pred = buf("y_pred", want_dense, (n,), torch.int64)
+    p_full = buf("p_full", want_dense, (n,), torch.float32)
+    out["count"] = status[:1]
+    out["n_flagged"] = cap
+    with torch.cuda.device(dev):
+        nbytes = int(lib.shm_hybrid4dof_workspace_bytes(vae._h, n, cap))
+        if nbytes < 0:
+            check(nbytes, "shm_hybrid4dof_workspace_bytes")
+        ws = _workspace(dev, nbytes, "hybrid4dof")
+        check(lib.shm_hybrid4dof_score(vae._h, cnn._h, C.byref(src.struct), n, _ptr(eps1), _ptr(eps2), float(np.float32(thr)), cap,
+                                       _ptr(score), _ptr(flag), _ptr(idx), _ptr(status), _ptr(logits), _ptr(label), _ptr(p_struct),
+                                       _ptr(y_pred), _ptr(p_full), _ptr(ws), ws.numel(), _stream()), "shm_hybrid4dof_score")
+    return out
+
+
+def hybridol_score(vae: VaeScorer, cnn: CnnOpenLab, src_gate: WindowSource, src_raw: WindowSource, eps: Optional[torch.Tensor],
+                   vae_thr: float, cnn_thr: float, n: Optional[int] = None, max_flagged: Optional[int] = None,
+                   want_flag: bool = True, want_compact: bool = True, want_dense: bool = True, out: Optional[dict] = None) -> dict:
+    """10_test_hybrid_pipeline.py:351-367 + stage2_predict_cnn (:265-302) + label scatter (:389-401) as ONE C call."""
+    lib = _lib.load()
+    n = src_gate.n_windows if n is None else int(n)
+    cap = n if max_flagged is None else min(n, int(max_flagged))
+    dev = src_gate.data.device
+    if src_raw.T != 200 or src_raw.D != 4:
+        raise ShmfastError("openLAB CNN expects windows of T=200, D=4")
+    if eps is not None:
+        _f32c(eps, "eps")
+        if eps.numel() < n * vae.Z:
+            raise ShmfastError("eps must hold [n, Z] values")
+    out = {} if out is None else out
+
+    def buf(name, want, shape, dt):
+        if not want:
+            return None
+        t = out.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=dt, device=dev)
+            out[name] = t
+        return t
+
+    score = buf("score", True, (n,), torch.float32)
+    flag = buf("flag", want_flag, (n,), torch.uint8)
+    idx = buf("idx", True, (max(n, 1),), torch.int32)
+    status = buf("status", True, (2,), torch.int32)
+    logits = buf("logits", want_compact, (cap, 2), torch.float32)
+    prob = buf("prob", want_compact, (cap,), torch.float64)
+    pred = buf("pred", want_compact, (cap,), torch.int64)
+    y_pred = buf("y_pred", want_dense, (n,), torch.int64)
+    prob_full = buf("prob_full", want_dense, (n,), torch.float64)
+    out["count"] = status[:1]
+    out["n_flagged"] = cap
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, int(lib.shm_hybridol_workspace_bytes(n, cap)), "hybridol")
+        check(lib.shm_hybridol_score(vae._h, cnn._h, C.byref(src_gate.struct), C.byref(src_raw.struct), n, _ptr(eps),
+                                     float(np.float32(vae_thr)), float(cnn_thr), cap, _ptr(score), _ptr(flag), _ptr(idx), _ptr(status),
+                                     _ptr(logits), _ptr(prob), _ptr(pred), _ptr(y_pred), _ptr(prob_full), _ptr(ws), ws.numel(),
+                                     _stream()), "shm_hybridol_score")
+    return out

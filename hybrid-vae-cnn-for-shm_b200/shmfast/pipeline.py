@@ -5,8 +5,12 @@
 * score_windows == full_mse_scores_batched (04_vae_thresholding.py:113-124) / recon_mse_per_window
 
 Everything between the input tensors and the result tensors runs as libshmfast kernels on the
-current stream; the only optional host round trip is the 4-byte flagged count (sync_count=True), used
-to size the flagged-subset buffers exactly like the reference's np.where does.
+current stream.  Two forms per stage:
+
+* `run(..., sync_count=True)`: the reference's control flow -- the 4-byte flagged count is read back once to size
+  the flagged-subset tensors exactly like np.where does;
+* `run_dense(...)`: ONE C call (shm_hybrid4dof_score / shm_hybridol_score), no host round trip; per-flagged outputs
+  have `max_flagged` rows and `status[1]` reports an overflow (count > max_flagged) instead of dropping windows silently.
 """
 from __future__ import annotations
 
@@ -41,13 +45,12 @@ class Hybrid4dof:
         windows with fresh noise (eps2[j] belongs to the j-th flagged window, the order in which the
         reference draws them) -> residual stack -> CNN -> label = argmax+1, p_struct."""
         n = src.n_windows if n is None else int(n)
+        if not sync_count:
+            return self.run_dense(src, eps1, eps2, n=n, max_flagged=max_flagged)
         out = self.vae.score(src, eps1, n=n, want_latent=True)     # mu / logvar feed the second pass (the encoder is deterministic)
         score = out["score"]
         flag, idx, count = ops.compact(score, self.thr)
-        if sync_count:
-            n_f = int(count.item())
-        else:
-            n_f = n if max_flagged is None else min(n, int(max_flagged))
+        n_f = int(count.item())
         res = dict(score=score, flag=flag, idx=idx, count=count, n_flagged=n_f)
         if n_f == 0:
             dev = score.device
@@ -61,18 +64,21 @@ class Hybrid4dof:
         res.update(logits=logits, label=label, p_struct=p_struct, cnn_in=second["cnn_in"])
         return res
 
+    def run_dense(self, src: WindowSource, eps1: Optional[torch.Tensor], eps2: Optional[torch.Tensor], n: Optional[int] = None,
+                  max_flagged: Optional[int] = None, out: Optional[dict] = None) -> dict:
+        """The whole loop as one C call; no host synchronisation.  eps2 must hold [max_flagged, Z] (or [n, Z]) rows.  The second
+        pass runs in bounded chunks inside the library, so max_flagged=None (= n) costs no extra memory.  `status` =
+        device int32[2] {flagged count, overflow}: check `status[1] == 0` when max_flagged < n."""
+        res = ops.hybrid4dof_score(self.vae, self.cnn, src, eps1, eps2, self.thr, n=n, max_flagged=max_flagged, out=out)
+        return res
+
     @staticmethod
     def scatter(res: dict, n: int):
         """y_pred / hyb_score_full of 06_test_full_pipeline.py:336,356,368-372 (0 for unflagged windows)."""
-        dev = res["score"].device
-        y_pred = torch.zeros((n,), dtype=torch.int64, device=dev)
-        p_full = torch.zeros((n,), dtype=torch.float32, device=dev)
-        k = int(res["count"].item())
-        if k:
-            sel = res["idx"][:k].long()
-            y_pred[sel] = res["label"][:k]
-            p_full[sel] = res["p_struct"][:k]
-        return y_pred, p_full
+        if "y_pred" in res and res["y_pred"].shape[0] == n:
+            return res["y_pred"], res["p_full"]
+        cap = int(res["label"].shape[0])
+        return ops.scatter_flagged_4dof(res["idx"], res["count"], cap, res["label"], res["p_struct"], n)
 
 
 class HybridOpenLab:
@@ -82,12 +88,11 @@ class HybridOpenLab:
     def run(self, src_gate: WindowSource, src_raw: WindowSource, eps: Optional[torch.Tensor], n: Optional[int] = None,
             sync_count: bool = True, max_flagged: Optional[int] = None) -> dict:
         n = src_gate.n_windows if n is None else int(n)
+        if not sync_count:
+            return self.run_dense(src_gate, src_raw, eps, n=n, max_flagged=max_flagged)
         score = self.vae.score(src_gate, eps, n=n)["score"]
         flag, idx, count = ops.compact(score, self.vae_thr)
-        if sync_count:
-            n_f = int(count.item())
-        else:
-            n_f = n if max_flagged is None else min(n, int(max_flagged))
+        n_f = int(count.item())
         res = dict(score=score, flag=flag, idx=idx, count=count, n_flagged=n_f)
         dev = score.device
         if n_f == 0:
@@ -95,5 +100,12 @@ class HybridOpenLab:
                        pred=torch.empty((0,), dtype=torch.int64, device=dev))
             return res
         logits, prob = self.cnn.forward(src_raw, n=n_f, idx=idx, n_dev=count, want_prob=True)
-        res.update(logits=logits, prob=prob, pred=(prob >= self.cnn_thr).to(torch.int64))
+        pred, y_pred, prob_full = ops.scatter_flagged_openlab(idx, count, n_f, prob, self.cnn_thr, n)
+        res.update(logits=logits, prob=prob, pred=pred, y_pred=y_pred, prob_full=prob_full)
         return res
+
+    def run_dense(self, src_gate: WindowSource, src_raw: WindowSource, eps: Optional[torch.Tensor], n: Optional[int] = None,
+                  max_flagged: Optional[int] = None, out: Optional[dict] = None) -> dict:
+        """One C call (shm_hybridol_score), no host synchronisation; `status` = device int32[2] {flagged count, overflow}."""
+        return ops.hybridol_score(self.vae, self.cnn, src_gate, src_raw, eps, self.vae_thr, self.cnn_thr, n=n,
+                                  max_flagged=max_flagged, out=out)

@@ -8,32 +8,17 @@ host-to-device copy and chunk i-1's device-to-host copy run on their own CUDA st
 kernels (two device input buffers, two pinned result sets, events between the three streams, no
 host synchronisation inside a chunk).
 
-`scatter_flagged` is `y_pred[idx] = label; hyb_score_full[idx] = p_struct` (06_test_full_pipeline.py:336,356,
-368-372) without reading the flagged count back: slots past the device-side count are routed to a dummy row.
+The dense label scatter (`y_pred[idx] = label; hyb_score_full[idx] = p_struct`, 06_test_full_pipeline.py:336,356,
+368-372) is a libshmfast kernel (`ops.scatter_flagged_4dof` / inside `shm_hybrid4dof_score`): the flagged count
+never leaves the device and no ATen kernel runs on the chunk path.
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Iterable, Sequence, Tuple
+from typing import Callable, Dict, Iterable, Sequence, Tuple  # noqa: F401
 
 import torch
 
 from ._lib import ShmfastError
-
-
-def scatter_flagged(idx: torch.Tensor, count: torch.Tensor, n: int, values: Sequence[torch.Tensor],
-                    dtypes: Sequence[torch.dtype]) -> Tuple[torch.Tensor, ...]:
-    """For each `values[k]` ([cap] device tensor, valid in [0, count)): a dense [n] tensor of `dtypes[k]` that is
-    0 except at idx[j] (j < count).  No host round trip: `count` stays on the device."""
-    cap = values[0].shape[0] if values else 0
-    dev = idx.device
-    j = torch.arange(cap, device=dev, dtype=torch.int32)
-    pos = torch.where(j < count.reshape(()).to(torch.int32), idx[:cap], torch.full((), n, device=dev, dtype=torch.int32)).long()
-    out = []
-    for v, dt in zip(values, dtypes):
-        full = torch.zeros((n + 1,), dtype=dt, device=dev)
-        full[pos] = v[:cap].to(dt)
-        out.append(full[:n])
-    return tuple(out)
 
 
 class HostStream:
@@ -41,8 +26,9 @@ class HostStream:
 
     step(dev_in, i) runs the device work of chunk i on the CURRENT stream and returns {name: device tensor};
     every returned tensor is copied into this chunk's pinned host buffer `name` (declared in `out_specs`).
-    `run` yields (i, {name: pinned host tensor}) once chunk i's results have landed; the host tensors are
-    reused `depth` chunks later, so consume (or copy) them before asking for the chunk after next.
+    `run` yields (i, {name: pinned host tensor}) once chunk i's results have landed.  There are `depth + 1` pinned
+    result sets, so the tensors of chunk i stay untouched while chunk i+1 is being fetched (its resume enqueues the
+    D2H copy of chunk i+2 into a third set); they are overwritten once chunk i+2 is requested.
     """
 
     def __init__(self, device: torch.device, in_shape: Sequence[int], out_specs: Dict[str, Tuple[Sequence[int], torch.dtype]],
@@ -55,9 +41,10 @@ class HostStream:
         self.s_in = torch.cuda.Stream(device)
         self.s_out = torch.cuda.Stream(device)
         self.dev_in = [torch.empty(tuple(in_shape), dtype=in_dtype, device=device) for _ in range(depth)]
-        self.host_out = [{k: torch.empty(tuple(shape), dtype=dt).pin_memory() for k, (shape, dt) in out_specs.items()} for _ in range(depth)]
-        mk = lambda: [torch.cuda.Event() for _ in range(depth)]
-        self.h2d_done, self.step_done, self.d2h_done = mk(), mk(), mk()
+        self.n_out = self.depth + 1
+        self.host_out = [{k: torch.empty(tuple(shape), dtype=dt).pin_memory() for k, (shape, dt) in out_specs.items()} for _ in range(self.n_out)]
+        mk = lambda m: [torch.cuda.Event() for _ in range(m)]
+        self.h2d_done, self.step_done, self.d2h_done = mk(depth), mk(depth), mk(self.n_out)
         self._keep = [None] * depth                   # device results stay referenced until their D2H copy has run
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -96,13 +83,14 @@ class HostStream:
             self.step_done[slot].record(compute)
             self._keep[slot] = outs
             self.s_out.wait_event(self.step_done[slot])
+            oslot = i % self.n_out
             with torch.cuda.stream(self.s_out):
-                for k, host in self.host_out[slot].items():
+                for k, host in self.host_out[oslot].items():
                     src = outs[k]
                     dst = host[tuple(slice(0, s) for s in src.shape)] if tuple(src.shape) != tuple(host.shape) else host
                     dst.copy_(src, non_blocking=True)
                     self.d2h_bytes += src.numel() * src.element_size()
-                self.d2h_done[slot].record(self.s_out)
+                self.d2h_done[oslot].record(self.s_out)
             if i >= 1:                                          # chunk i-1's results landed while chunk i was being issued / run
                 yield self._deliver(i - 1)
             i += 1
@@ -110,7 +98,7 @@ class HostStream:
             yield self._deliver(i - 1)
 
     def _deliver(self, i: int):
-        slot = i % self.depth
-        self.d2h_done[slot].synchronize()
-        self._keep[slot] = None
-        return i, self.host_out[slot]
+        oslot = i % self.n_out
+        self.d2h_done[oslot].synchronize()
+        self._keep[i % self.depth] = None
+        return i, self.host_out[oslot]

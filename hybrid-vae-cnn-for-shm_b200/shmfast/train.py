@@ -51,8 +51,10 @@ class VaeTrainHandle:
             raise ShmfastError("bad VAE configuration")
         h = C.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        check(self._lib.shm_vae_trainer_create(C.byref(h), C.byref(cfg), self.T, self.max_batch, idx), "shm_vae_trainer_create")
+        with torch.cuda.device(self.device):
+            check(self._lib.shm_vae_trainer_create(C.byref(h), C.byref(cfg), self.T, self.max_batch, idx), "shm_vae_trainer_create")
         self._h = h
+        self.generation = 0            # id of the forward whose activations the workspace currently holds
 
     def forward(self, params: torch.Tensor, x: torch.Tensor, eps: torch.Tensor, drop_enc: Optional[torch.Tensor] = None,
                 drop_dec: Optional[torch.Tensor] = None, drop_p: float = 0.0, want_xhat: bool = True):
@@ -74,6 +76,7 @@ class VaeTrainHandle:
         with torch.cuda.device(x.device):
             check(self._lib.shm_vae_train_forward(self._h, _ptr(params), _ptr(x), B, _ptr(eps), _ptr(drop_enc), _ptr(drop_dec),
                                                   float(drop_p), _ptr(xhat), _ptr(mu), _ptr(lv), _stream()), "shm_vae_train_forward")
+        self.generation += 1
         return xhat, mu, lv
 
     def backward(self, params: torch.Tensor, d_xhat: torch.Tensor, d_mu: Optional[torch.Tensor], d_lv: Optional[torch.Tensor],
@@ -160,12 +163,16 @@ class VaeTrainFunction(torch.autograd.Function):
         flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
         xhat, mu, lv = handle.forward(flat, x.detach().contiguous(), eps.contiguous(), drop_enc, drop_dec, drop_p)
         ctx.handle, ctx.flat = handle, flat
+        ctx.generation = handle.generation          # the single workspace holds THIS forward's activations
         ctx.shapes = [p.shape for p in params]
         ctx.x_shape = x.shape
         return xhat, mu, lv
 
     @staticmethod
     def backward(ctx, d_xhat, d_mu, d_lv):
+        if ctx.generation != ctx.handle.generation:
+            raise ShmfastError("backward of a stale graph: another train-mode forward of this model overwrote the activation "
+                               "workspace (one backward per forward; call backward before the next forward)")
         if d_xhat is None:
             d_xhat = ctx.flat.new_zeros(ctx.x_shape)
         g = ctx.handle.backward(ctx.flat, d_xhat.contiguous().float(), None if d_mu is None else d_mu.contiguous().float(),

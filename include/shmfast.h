@@ -128,6 +128,7 @@ int shm_vae_create(shm_vae** out, const shm_vae_cfg* cfg_host, const shm_vae_wei
 int shm_vae_update_weights(shm_vae* h, const shm_vae_weights* w_host, void* stream);
 int shm_vae_destroy(shm_vae* h);
 int shm_vae_engine(const shm_vae* h);    /* the engine actually selected */
+int shm_vae_get_cfg(const shm_vae* h, shm_vae_cfg* out_host);   /* the handle's shape; engine = the one selected */
 /* Profiling aid (tensor-core engine): the first call enables per-CTA cycle counters of the MMA-issuer warp,
  * later calls copy them out: out_host[cta*8 + {0: wait weights, 1: wait input, 2: wait accumulator drain,
  * 3: wait h_t, 4..7: total cycles of pass 0..3}], accumulated over launches. */
@@ -279,6 +280,41 @@ int shm_cnnol_forward(shm_cnnol* h, const shm_window_src* src_host, const int32_
  * windows per internal chunk) or SHM_ENGINE_FP32 (everything on the CUDA cores, one CTA per window, no workspace). */
 int shm_cnnol_set_engine(shm_cnnol* h, int engine);
 int shm_cnnol_engine(const shm_cnnol* h);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused hybrid loops: the reference's script-level hot loops as ONE call on one stream.  No host synchronisation:
+ * the flagged count stays on the device; per-flagged scratch is bounded (the 4DOF second pass runs in chunks of
+ * 65,536 flagged windows), so `max_flagged` may be as large as n.
+ *
+ * shm_hybrid4dof_score == eval_group (4DOF/Scripts/06_test_full_pipeline.py:327-383): score pass (eps1[n,Z]) ->
+ *   `mse > thr` + np.where (:350-351) -> SECOND VAE pass on the flagged windows with fresh noise (eps2[j] belongs to
+ *   the j-th flagged window, :360-363) -> stack([z, (z-zhat)^2]) (:364-365) -> CNN (:366) -> cls = argmax,
+ *   y_pred[sel] = cls+1, hyb_score_full[sel] = softmax[:,1] (:367-372).
+ *     score[n], flag[n] (opt), idx[n] (first status[0] entries valid, ascending);
+ *     status: device int32[2] = {flagged count, 1 if count > max_flagged (windows past max_flagged were NOT attributed)};
+ *     logits[max_flagged,2], label[max_flagged], p_struct[max_flagged]: optional per-flagged outputs;
+ *     y_pred[n] int64 / p_full[n] fp32: optional dense outputs, 0 for windows that were not flagged (:336,356).
+ * shm_hybridol_score == 10_test_hybrid_pipeline.py:351-367 (gate on src_gate) + stage2_predict_cnn (:265-302, CNN on
+ *   src_raw[flagged], prob_st = softmax[:,1] as fp64, pred_bin = prob_st >= cnn_thr) + the label scatter (:389-401):
+ *     prob[max_flagged], pred_bin[max_flagged]: optional per-flagged outputs;
+ *     y_pred[n]: 0 = not flagged, 1 = sensor fault (pred_bin 0), 2 = structural (pred_bin 1); prob_full[n] fp64.
+ * shm_scatter_flagged_*: only the scatter step, for callers that ran the stages themselves (`count` may be NULL:
+ *   all `cap` entries are valid).  Dense outputs are zero-filled first.
+ * ------------------------------------------------------------------------------------------- */
+int64_t shm_hybrid4dof_workspace_bytes(const shm_vae* vae, int64_t n, int64_t max_flagged);
+int shm_hybrid4dof_score(shm_vae* vae, shm_cnn4dof* cnn, const shm_window_src* src_host, int64_t n, const float* eps1,
+                         const float* eps2, float thr, int64_t max_flagged, float* score, uint8_t* flag, int32_t* idx,
+                         int32_t* status, float* logits, int64_t* label, float* p_struct, int64_t* y_pred, float* p_full,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+int64_t shm_hybridol_workspace_bytes(int64_t n, int64_t max_flagged);
+int shm_hybridol_score(shm_vae* vae, shm_cnnol* cnn, const shm_window_src* src_gate_host, const shm_window_src* src_raw_host,
+                       int64_t n, const float* eps, float vae_thr, double cnn_thr, int64_t max_flagged, float* score,
+                       uint8_t* flag, int32_t* idx, int32_t* status, float* logits, double* prob, int64_t* pred_bin,
+                       int64_t* y_pred, double* prob_full, void* workspace, int64_t workspace_bytes, void* stream);
+int shm_scatter_flagged_4dof(const int32_t* idx, const int32_t* count, int64_t cap, const int64_t* label, const float* p_struct,
+                             int64_t n, int64_t* y_pred, float* p_full, void* stream);
+int shm_scatter_flagged_openlab(const int32_t* idx, const int32_t* count, int64_t cap, const double* prob, double cnn_thr,
+                                int64_t n, int64_t* pred_bin, int64_t* y_pred, double* prob_full, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * openLAB extraction front-end: what feeds the hybrid path.  One run's parsed catman

@@ -249,22 +249,11 @@ def test_kl_anneal_matches_reference_formula():
         assert abs(train.kl_anneal_sigmoid(epoch, 50) - ref) < 1e-15
 
 
-def test_scatter_flagged_is_the_reference_scatter_without_a_count_readback():
-    """shmfast.stream.scatter_flagged == `y_pred[idx] = label; hyb_score_full[idx] = p_struct` (06_test_full_pipeline.py:336,356,368-372);
-    slots past the (device-side) count hold garbage and must not land anywhere.  Pure tensor code: checked on CPU tensors."""
-    from shmfast.stream import HostStream, scatter_flagged
-    g = torch.Generator().manual_seed(11)
-    n, cap = 257, 64
-    for k in (0, 1, 37, cap):
-        idx_ok = torch.sort(torch.randperm(n, generator=g)[:k]).values.to(torch.int32)
-        idx = torch.randint(0, n, (cap,), generator=g, dtype=torch.int32)             # garbage beyond k (in range on purpose)
-        idx[:k] = idx_ok
-        label = torch.randint(1, 3, (cap,), generator=g)
-        p = torch.rand((cap,), generator=g, dtype=torch.float64)
-        y, pf = scatter_flagged(idx, torch.tensor([k], dtype=torch.int32), n, [label, p], [torch.int64, torch.float64])
-        y_ref = np.zeros(n, np.int64); p_ref = np.zeros(n, np.float64)
-        y_ref[idx_ok.numpy()] = label[:k].numpy(); p_ref[idx_ok.numpy()] = p[:k].numpy()
-        assert np.array_equal(y.numpy(), y_ref) and np.array_equal(pf.numpy(), p_ref)
+def test_host_stream_and_dense_entries_have_no_cpu_path():
+    """The streaming helper and the fused hybrid entries refuse CPU tensors: there is no fallback to compute elsewhere."""
     from shmfast import ops
-    with pytest.raises(ops.ShmfastError):                                              # the streaming helper has no CPU path either
+    from shmfast.stream import HostStream
+    with pytest.raises(ops.ShmfastError):
         HostStream(torch.device("cpu"), (8, 4), {"score": ((8,), torch.float32)})
+    with pytest.raises(ops.ShmfastError):
+        ops.scatter_flagged_4dof(torch.zeros(4, dtype=torch.int32), None, 4, torch.zeros(4, dtype=torch.int64), torch.zeros(4), 8)

@@ -1,0 +1,200 @@
+"""Script-level checks against the reference's OWN, unmodified files (north_star: "the 03/04/06 (4DOF) and 04/05/10
+(openLAB) script entry points stay a drop-in").  The files are the byte-for-byte copies `oracle/stage_ref.py` puts into the
+git-ignored `oracle/_ref/` at build time (or /root/reference itself in the build container); without them the tests skip.
+
+CPU (`-m "not gpu"`): the oracle is pinned against the unmodified `06_test_full_pipeline.main()` at script level.
+GPU (`-m gpu`): every script is executed twice on cuda:0 under the same seed -- once with the reference `Models/`
+(cuDNN LSTM / conv), once with `Models/` replaced by the three-line shmfast stubs of INTEGRATION.md -- and compared:
+scores <= 1e-4 relative, flags / labels / confusion matrices identical outside the tolerance band (band counted).
+"""
+import json
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O
+from oracle import ref_driver as R
+from shmfast import synth
+
+REL_TOL = 1e-4
+
+needs_ref = pytest.mark.skipif(R.ref_root() is None, reason="reference files not staged (oracle/stage_ref.py runs in the build container)")
+
+
+def _rel(a, b, floor=1e-6):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def _trained(golden_dir):
+    p = golden_dir / "trained_4dof.npz"
+    if not p.exists():
+        pytest.skip("trained fixture not generated")
+    g = np.load(p)
+    vae_sd = {k[4:]: g[k] for k in g.files if k.startswith("vae.")}
+    cnn_sd = {k[4:]: g[k] for k in g.files if k.startswith("cnn.")}
+    return g, vae_sd, cnn_sd
+
+
+def _small_splits():
+    """Two checked-in runs per class (6 CSVs x 202 test windows): seconds on the CPU."""
+    root = R.ref_root()
+    full = json.loads((root / R.DIR4 / "Data/processed/run_splits.json").read_text())
+    return {k: {"files": full[k]["files"][:2]} for k in ("normal", "sensor_fault", "structural_fault")}
+
+
+@needs_ref
+def test_staged_files_are_byte_identical_to_the_manifest():
+    root = R.ref_root()
+    if root != R.STAGED:
+        from oracle import stage_ref
+        assert stage_ref.stage() == R.STAGED
+    import hashlib
+    man = json.loads((R.STAGED / "MANIFEST.json").read_text())
+    assert "4DOF/Scripts/06_test_full_pipeline.py" in man and "20250506_openLAB_tests/Codes/10_test_hybrid_pipeline.py" in man
+    for rel, dig in man.items():
+        assert hashlib.sha256((R.STAGED / rel).read_bytes()).hexdigest() == dig, rel
+
+
+@needs_ref
+def test_oracle_equals_unmodified_06_main_on_cpu(golden_dir, tmp_path):
+    """oracle.np_oracle.hybrid_4dof vs the reference script's eval_group (06_test_full_pipeline.py:327-383), run through its
+    unmodified main() with the reference Models on the CPU; eps streams reproduced from set_seed(42) in call order."""
+    g, vae_sd, cnn_sd = _trained(golden_dir)
+    thr = float(g["thr"])
+    splits = _small_splits()
+    tree = R.Tree4dof(tmp_path / "ref", "reference", vae_sd, cnn_sd, g["mean"], g["std"], thr, splits=splits)
+    (tree.root / "Data" / "raw").symlink_to(R.ref_root() / R.DIR4 / "Data" / "raw")
+    with torch.no_grad():
+        out = R.run_06_main(tree)
+    # the oracle on the same windows, same eps order: per group all score batches, then all flagged batches (06:340-372)
+    mean, std = g["mean"].astype(np.float32), O.guard_std_4dof(g["std"].astype(np.float32))
+    torch.manual_seed(42)
+    # main() builds both models AFTER set_seed (06:277,295-309): their default initialisation consumes the generator first
+    RefVAE, RefCNN = R.reference_models("4dof")
+    RefVAE(input_dim=12, latent_dim=16, hidden_dim=128, num_layers=2, dropout=0.3)
+    RefCNN(input_channels=2, num_classes=2, dropout_rate=0.5)
+    scores, ypred, hyb = [], [], []
+    for key in ("normal", "sensor_fault", "structural_fault"):
+        W = []
+        for fp in splits[key]["files"]:
+            X = np.loadtxt(str(R.ref_root() / R.DIR4 / fp), delimiter=",", skiprows=1).astype(np.float32)
+            W.append(O.make_windows(O.slice_frac(X, (0.7, 1.0)), 100, 1))
+        Z = O.normalize_windows_4dof(np.concatenate(W, axis=0), mean, std)
+        n = Z.shape[0]
+        eps1 = np.concatenate([torch.randn(min(512, n - i), 16).numpy() for i in range(0, n, 512)])
+        s = O.vae_scores_batched(vae_sd, Z, eps1, 512, np.float32)
+        k = int((s > np.float32(thr)).sum())
+        eps2 = np.concatenate([torch.randn(min(512, k - j), 16).numpy() for j in range(0, k, 512)]) if k else np.zeros((0, 16), np.float32)
+        r = O.hybrid_4dof(vae_sd, cnn_sd, Z, eps1, eps2, thr, dtype=np.float32)
+        scores.append(r["score"]); ypred.append(r["y_pred"]); hyb.append(r["p_struct"])
+    score = np.concatenate(scores)
+    assert score.shape == out["gate_scores"].shape
+    assert _rel(score, out["gate_scores"]) < 2e-5
+    band = int((np.abs(out["gate_scores"] - thr) <= REL_TOL * thr).sum())
+    assert band == 0
+    y = np.concatenate(ypred)
+    yt = np.concatenate([np.full(s.shape[0], c) for c, s in enumerate(scores)])
+    cm = np.zeros((3, 3), np.int64)
+    np.add.at(cm, (yt, y), 1)
+    assert cm.tolist() == out["metrics"]["confusion_matrix_counts"]
+    assert np.allclose(np.concatenate(hyb), out["hyb_scores"], atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU: reference Models (cuDNN) vs the shmfast stubs, same script, same seed
+# ------------------------------------------------------------------------------------------------------------
+@needs_ref
+@pytest.mark.gpu
+def test_06_main_reference_models_vs_shmfast_stubs(cuda_dev, golden_dir, tmp_path):
+    """The unmodified 06_test_full_pipeline.main() on the repo's 4040 real test windows with reference-trained weights."""
+    g, vae_sd, cnn_sd = _trained(golden_dir)
+    thr = float(g["thr"])
+    outs = {}
+    for kind in ("reference", "shmfast"):
+        tree = R.Tree4dof(tmp_path / kind, kind, vae_sd, cnn_sd, g["mean"], g["std"], thr)
+        outs[kind] = R.run_06_main(tree)
+        if kind == "shmfast":
+            mod_names = [m for m in sys.modules if m.startswith("Scripts.Models")]
+            assert any("temporal_vae" in m for m in mod_names)
+            assert sys.modules["Scripts.Models.temporal_vae"].TemporalVAE.__module__.startswith("shmfast.models")
+    a, b = outs["reference"], outs["shmfast"]
+    assert a["gate_scores"].shape == b["gate_scores"].shape == (4040,)
+    # same Philox stream: the shim draws eps where the reference's reparameterize does (temporal_vae.py:60-63)
+    assert _rel(b["gate_scores"], a["gate_scores"]) < REL_TOL
+    band = np.abs(a["gate_scores"] - thr) <= REL_TOL * thr
+    flags_a, flags_b = a["gate_scores"] > np.float32(thr), b["gate_scores"] > np.float32(thr)
+    assert np.array_equal(flags_a[~band], flags_b[~band]), f"flags differ outside the band ({int(band.sum())} windows inside)"
+    if int(band.sum()) == 0:
+        assert a["metrics"]["confusion_matrix_counts"] == b["metrics"]["confusion_matrix_counts"]
+        assert a["metrics"]["gate"]["gate_stats"] == b["metrics"]["gate"]["gate_stats"]
+        same = flags_a
+        assert np.allclose(b["hyb_scores"][same], a["hyb_scores"][same], atol=2e-4)
+        # argmax labels: structural iff p_struct > 0.5; identical unless a probability sits at the decision boundary
+        near = np.abs(a["hyb_scores"] - 0.5) < 2e-4
+        assert np.array_equal((a["hyb_scores"] > 0.5)[~near], (b["hyb_scores"] > 0.5)[~near])
+    print(f"06 main: score rel err {_rel(b['gate_scores'], a['gate_scores']):.2e}, band {int(band.sum())}, "
+          f"reference eval {a['eval_seconds']:.2f}s vs stubs {b['eval_seconds']:.2f}s")
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_04_full_mse_scores_batched_reference_vs_stub(cuda_dev, golden_dir, tmp_path):
+    """`full_mse_scores_batched` (04_vae_thresholding.py:113-124) imported from the unmodified script, P99 threshold rule (:283)."""
+    g, vae_sd, cnn_sd = _trained(golden_dir)
+    Z = g["Z"]
+    res = {}
+    for kind in ("reference", "shmfast"):
+        tree = R.Tree4dof(tmp_path / kind, kind, vae_sd, cnn_sd, g["mean"], g["std"], float(g["thr"]))
+        mod = tree.load("04_vae_thresholding")
+        vae = mod.TemporalVAE(input_dim=12, latent_dim=16, hidden_dim=128, num_layers=2, dropout=0.3).to(cuda_dev)
+        vae.load_state_dict(torch.load(str(tree.root / "models" / "temporal_vae_state_dict.pt"), map_location=cuda_dev))
+        vae.eval()
+        mod.set_seed(42)
+        s = mod.full_mse_scores_batched(vae, Z, cuda_dev, 100)            # 240 windows in batches of 100 (ragged last batch)
+        res[kind] = (s, float(np.percentile(s, mod.PCTL)))
+    assert res["shmfast"][0].dtype == res["reference"][0].dtype and res["shmfast"][0].shape == (Z.shape[0],)
+    assert _rel(res["shmfast"][0], res["reference"][0]) < REL_TOL
+    assert abs(res["shmfast"][1] - res["reference"][1]) <= REL_TOL * abs(res["reference"][1])
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_10_openlab_functions_reference_vs_stub(cuda_dev, golden_dir, tmp_path):
+    """`recon_mse_per_window` (10_test_hybrid_pipeline.py:240-251), `standardize` (:233-237) and `stage2_predict_cnn` (:265-302)
+    imported from the unmodified script, on real openLAB windows (NaN-bearing X_raw rows included)."""
+    g = np.load(golden_dir / "openlab_real_windows.npz")
+    Xc, Xr = g["X_clean"], g["X_raw"]
+    vae_sd = synth.stage_vae_weights("openlab", seed=int(g["seed"]), scale=2.0)
+    cnn_sd = synth.cnnol_weights(seed=int(g["seed"]))
+    vmu, vsd = g["vae_mu"].astype(np.float32), g["vae_sd"].astype(np.float32)
+    cmu, csd = g["cnn_mu"].astype(np.float32), g["cnn_sd"].astype(np.float32)
+    art = R.cnn_artifacts_openlab(tmp_path / "art", cnn_sd, cmu, csd, 0.5)
+    res = {}
+    for kind in ("reference", "shmfast"):
+        tree = R.TreeOpenLab(tmp_path / kind, kind)
+        try:
+            mod = tree.load("10_test_hybrid_pipeline")
+            vae = mod.VAE(input_dim=3, latent_dim=8, hidden_dim=64, num_layers=1, dropout=0.2).to(cuda_dev)
+            vae.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in vae_sd.items()})
+            vae.eval()
+            Xg = mod.standardize(Xc[:, :, [1, 2, 3]], vmu, vsd, clip=mod.CLIP_Z)
+            torch.manual_seed(42)
+            mse = mod.recon_mse_per_window(vae, Xg, device=cuda_dev, batch_size=mod.BATCH_SIZE)
+            res[kind] = dict(mse=mse)
+        finally:
+            pass
+        if kind == "reference":
+            thr = float(np.sort(mse)[int(0.6 * mse.size)]) + 1e-3          # ~40 % flagged
+        mask = res["reference"]["mse"] > thr                               # the same routed set for both runs
+        pred, prob, t = mod.stage2_predict_cnn(Xr, mask, art)
+        res[kind].update(pred=pred, prob=prob)
+        tree.release()
+    a, b = res["reference"], res["shmfast"]
+    assert _rel(b["mse"], a["mse"]) < REL_TOL
+    assert a["prob"].dtype == b["prob"].dtype == np.float64 and a["prob"].shape == b["prob"].shape
+    assert np.allclose(b["prob"], a["prob"], rtol=REL_TOL, atol=2e-4)
+    near = np.abs(a["prob"] - 0.5) < 2e-4
+    assert np.array_equal(a["pred"][~near], b["pred"][~near])
