@@ -12,6 +12,7 @@
 //   * heads (LayerNorm, mu/logvar, reparameterisation, latent->hidden) are one small kernel per direction.
 #include <new>
 #include "common.cuh"
+#include "gemm.cuh"
 
 namespace shm {
 
@@ -166,8 +167,16 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmArgs g) {
     }
 }
 
-static int gemm(cudaStream_t st, const float* A, long long a_ms, long long a_ks, const float* B, long long b_ks, long long b_ns,
-                float* C, long long ldc, int M, int N, int K, const float* bias1, const float* bias2, bool splitk) {
+int sgemm(cudaStream_t st, const float* A, long long a_ms, long long a_ks, const float* B, long long b_ks, long long b_ns, float* C,
+          long long ldc, int M, int N, int K, const float* bias1, const float* bias2, bool splitk);
+
+static inline int gemm(cudaStream_t st, const float* A, long long a_ms, long long a_ks, const float* B, long long b_ks, long long b_ns,
+                       float* C, long long ldc, int M, int N, int K, const float* bias1, const float* bias2, bool splitk) {
+    return sgemm(st, A, a_ms, a_ks, B, b_ks, b_ns, C, ldc, M, N, K, bias1, bias2, splitk);
+}
+
+int sgemm(cudaStream_t st, const float* A, long long a_ms, long long a_ks, const float* B, long long b_ks, long long b_ns, float* C,
+          long long ldc, int M, int N, int K, const float* bias1, const float* bias2, bool splitk) {
     if (M <= 0 || N <= 0 || K <= 0) return SHM_OK;
     GemmArgs g{A, a_ms, a_ks, B, b_ks, b_ns, C, ldc, M, N, K, bias1, bias2, K, splitk ? 1 : 0};
     const bool narrow = N <= 16;
@@ -631,16 +640,18 @@ __global__ void sumsq_kernel(const float* __restrict__ g, size_t n, float* __res
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            size_t n, float lr, float b1, float b2, float omb1, float omb2, float eps, float wd, float max_norm,
-                            float grad_scale, float bc1, float bc2_sqrt, float* __restrict__ norm2) {
+                            size_t n, float lr, float b1, float b2, float omb1, float omb2, float eps, float wd, int decoupled,
+                            float max_norm, float grad_scale, float bc1, float bc2_sqrt, float* __restrict__ norm2) {
     const float total_norm = sqrtf(norm2[0]) * grad_scale;
     float coef = 1.f;
     if (max_norm > 0.f) coef = fminf(1.f, max_norm / (total_norm + 1e-6f));
     const float gs = grad_scale * coef;
     const float step = lr / bc1;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float pv = p[i];
-        const float gr = fmaf(wd, pv, g[i] * gs);
+        float pv = p[i];
+        float gr = g[i] * gs;
+        if (decoupled) pv *= 1.f - lr * wd;                          // AdamW: param.mul_(1 - lr * weight_decay)
+        else gr = fmaf(wd, pv, gr);                                  // Adam: weight decay added to the gradient
         const float mv = fmaf(b1, m[i], omb1 * gr);                 // exp_avg.lerp_(grad, 1-beta1); 1-beta in double like torch
         const float vv = fmaf(b2, v[i], omb2 * gr * gr);
         m[i] = mv; v[i] = vv;
@@ -977,15 +988,14 @@ extern "C" int shm_vae_elbo_grad(const float* x, const float* xhat, const float*
     return SHM_OK;
 }
 
-extern "C" int shm_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t step,
-                                  float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
-                                  float grad_scale, float* norm2, void* stream) {
+namespace shm {
+int adam_step(cudaStream_t st, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step, float lr,
+              float beta1, float beta2, float eps, float weight_decay, int decoupled, float max_norm, float grad_scale, float* norm2) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || !norm2 || n < 1 || step < 1) return SHM_ERR_ARG;
     int dev = 0;
     SHM_CUDA(cudaGetDevice(&dev));
     int rc = check_device(dev);
     if (rc != SHM_OK) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
     SHM_CUDA(cudaMemsetAsync(norm2, 0, 2 * sizeof(float), st));
     const int grid = (int)((n + 255) / 256 < 296 ? (n + 255) / 256 : 296);
     sumsq_kernel<<<grid, 256, 0, st>>>(grads, (size_t)n, norm2);
@@ -993,7 +1003,23 @@ extern "C" int shm_adam_clip_step(float* params, const float* grads, float* exp_
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
     adam_kernel<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (size_t)n, lr, beta1, beta2, (float)(1.0 - (double)beta1),
-                                      (float)(1.0 - (double)beta2), eps, weight_decay, max_norm, grad_scale, (float)bc1, (float)sqrt(bc2), norm2);
+                                      (float)(1.0 - (double)beta2), eps, weight_decay, decoupled, max_norm, grad_scale, (float)bc1,
+                                      (float)sqrt(bc2), norm2);
     SHM_LAUNCH_CHECK();
     return SHM_OK;
+}
+}  // namespace shm
+
+extern "C" int shm_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t step,
+                                  float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
+                                  float grad_scale, float* norm2, void* stream) {
+    return shm::adam_step((cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, weight_decay, 0, max_norm,
+                          grad_scale, norm2);
+}
+
+extern "C" int shm_adamw_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t step,
+                                   float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
+                                   float grad_scale, float* norm2, void* stream) {
+    return shm::adam_step((cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, weight_decay, 1, max_norm,
+                          grad_scale, norm2);
 }

@@ -12,6 +12,7 @@ SHM_MAX_D = 16
 SHM_MAX_L = 2
 
 ENGINE_AUTO, ENGINE_FP32, ENGINE_TC_BF16X3 = 0, 1, 2
+CNN_4DOF, CNN_OPENLAB = 0, 1
 
 _fp = C.POINTER(C.c_float)
 _vp = C.c_void_p
@@ -93,6 +94,14 @@ SIGNATURES = {
     "shm_vae_elbo_grad": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_float, _vp, _vp, _vp, _vp, _vp]),
     "shm_adam_clip_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_float, C.c_float, C.c_float, _vp, _vp]),
+    "shm_adamw_clip_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
+                                      C.c_float, C.c_float, C.c_float, _vp, _vp]),
+    "shm_cnn_param_count": (C.c_int64, [C.c_int]),
+    "shm_cnn_trainer_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int32, C.c_int]),
+    "shm_cnn_trainer_destroy": (C.c_int, [_vp]),
+    "shm_cnn_train_forward": (C.c_int, [_vp, _vp, _vp, C.c_int32, _vp, C.c_float, _vp, C.c_float, _vp, _vp]),
+    "shm_cnn_train_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "shm_cnn_loss_grad": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_float, _vp, _vp, _vp]),
     "shm_compact_workspace_bytes": (C.c_int64, [C.c_int64]),
     "shm_compact": (C.c_int, [_vp, C.c_float, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "shm_cnn4dof_create": (C.c_int, [C.POINTER(_vp), C.POINTER(Cnn4dofWeights), C.c_int]),

@@ -124,9 +124,45 @@ class _HandleModule(nn.Module):
 
     _handle_cls = None
 
+    ARCH = None          # _lib.CNN_4DOF / _lib.CNN_OPENLAB
+    drop_p = 0.0
+
     def _init_handle(self):
         self._handle = None
         self._sig = None
+        self._trainer = None
+
+    def _bn_buffers(self):
+        return []
+
+    def _train_forward(self, x: torch.Tensor) -> torch.Tensor:
+        """train() mode (05_train_cnn.py:272, 06_train_cnn.py:414): forward with batch statistics / dropout on the training kernels,
+        bridged into autograd so the reference's `loss.backward()` / `optimizer.step()` lines run unchanged.  The dropout keep-mask
+        is drawn with torch's generator on the device; BatchNorm running statistics are updated like nn.BatchNorm2d does."""
+        from .. import cnn_train as _ct
+        if not x.is_cuda:
+            raise ShmfastError("input is a CPU tensor: libshmfast has no CPU fallback")
+        x = x.detach().to(torch.float32).contiguous()
+        B = x.shape[0]
+        h = self._trainer
+        if h is None or h.max_batch < B or h.device != x.device:
+            if h is not None:
+                h.close()
+            h = self._trainer = _ct.CnnTrainHandle(self.ARCH, B, x.device)
+        mask = _ct.draw_dropout_mask(B, float(self.drop_p), x.device)
+        bufs = self._bn_buffers()
+        running = torch.cat([b.reshape(-1) for b in bufs]).contiguous() if bufs else None
+        logits = _ct.CnnTrainFunction.apply(h, x, running, 0.1, mask, float(self.drop_p) if mask is not None else 0.0, *self.parameters())
+        if bufs:
+            o = 0
+            with torch.no_grad():
+                for b in bufs:
+                    b.copy_(running[o:o + b.numel()].view_as(b))
+                    o += b.numel()
+                for m in self.modules():
+                    if isinstance(m, nn.BatchNorm2d):
+                        m.num_batches_tracked += 1
+        return logits
 
     def handle(self):
         dev = next(self.parameters()).device
@@ -146,7 +182,4 @@ class _HandleModule(nn.Module):
     def _eval_only(self, x):
         if not x.is_cuda:
             raise ShmfastError("input is a CPU tensor: libshmfast has no CPU fallback")
-        if self.training:
-            raise NotImplementedError("the CNN shims implement the inference path (eval mode); CNN training is out of "
-                                      "scope of the hot path (SURVEY.md section 2)")
         return x.detach().to(torch.float32).contiguous()

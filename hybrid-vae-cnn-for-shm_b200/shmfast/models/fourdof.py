@@ -27,9 +27,11 @@ __all__ = ["TemporalVAE", "VAE", "CNN", "CNNClassifier", "SEQ_LEN", "NUM_FEATURE
 class CNN(_HandleModule):
     """4DOF/Scripts/Models/cnn_model.py:8-51.  Input (B, 2, 100, 12) -> logits (B, 2)."""
     _handle_cls = ops.Cnn4dof
+    ARCH = 0             # _lib.CNN_4DOF
 
     def __init__(self, input_channels: int = 2, num_classes: int = 2, dropout_rate: float = 0.5):
         super().__init__()
+        self.drop_p = float(dropout_rate)
         if input_channels != 2 or num_classes != 2:
             raise ops.ShmfastError("the 4DOF CNN kernels are specialised to input_channels=2, num_classes=2")
         self.conv1 = nn.Sequential(nn.Conv2d(input_channels, 16, kernel_size=3, padding=1), nn.BatchNorm2d(16), nn.ReLU(),
@@ -48,7 +50,14 @@ class CNN(_HandleModule):
             if m.bias is not None:
                 nn.init.zeros_(m.bias)
 
+    def _bn_buffers(self):
+        return [self.conv1[1].running_mean, self.conv1[1].running_var, self.conv2[1].running_mean, self.conv2[1].running_var]
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            if x.dim() != 4 or tuple(x.shape[1:]) != (2, SEQ_LEN, NUM_FEATURES):
+                raise ops.ShmfastError(f"4DOF CNN expects [B,2,100,12], got {tuple(x.shape)}")
+            return self._train_forward(x)
         return self.handle().forward(self._eval_only(x))
 
 

@@ -23,9 +23,11 @@ class VAE(TemporalVAEBase):
 class CNN(_HandleModule):
     """Codes/Models/cnn_model.py:8-57.  Input (B, 1, 200, 4) -> logits (B, 2) for [SF, E]."""
     _handle_cls = ops.CnnOpenLab
+    ARCH = 1             # _lib.CNN_OPENLAB
 
     def __init__(self, input_channels=1, num_classes=2, dropout_rate=0.4):
         super().__init__()
+        self.drop_p = float(dropout_rate)
         if input_channels != 1 or num_classes != 2:
             raise ops.ShmfastError("the openLAB CNN kernels are specialised to input_channels=1, num_classes=2")
 
@@ -52,6 +54,10 @@ class CNN(_HandleModule):
                 nn.init.zeros_(m.bias)
 
     def forward(self, x):
+        if self.training:
+            if x.dim() != 4 or tuple(x.shape[1:]) != (1, SEQ_LEN, NUM_FEATURES):
+                raise ops.ShmfastError(f"openLAB CNN expects [B,1,200,4], got {tuple(x.shape)}")
+            return self._train_forward(x)
         x = self._eval_only(x)
         if x.dim() != 4 or tuple(x.shape[1:]) != (1, SEQ_LEN, NUM_FEATURES):
             raise ops.ShmfastError(f"openLAB CNN expects [B,1,200,4], got {tuple(x.shape)}")

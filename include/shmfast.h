@@ -213,6 +213,41 @@ int shm_adam_clip_step(float* params, const float* grads, float* exp_avg, float*
                        float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                        float* norm2, void* stream);
 
+/* AdamW twin of shm_adam_clip_step (decoupled weight decay: param *= 1 - lr*weight_decay before the Adam update), the optimiser of
+ * openLAB Codes/06_train_cnn.py:395 (AdamW lr 3e-4 wd 1e-4) after clip_grad_norm_(2.0) (:417). */
+int shm_adamw_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t step,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                        float* norm2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CNN training steps.
+ *   SHM_CNN_4DOF    : 4DOF/Scripts/Models/cnn_model.py:16-51 in train() mode (BatchNorm batch statistics + running-stat
+ *                     update, Dropout 0.5 after fc1); loop 4DOF/Scripts/05_train_cnn.py:266-281
+ *                     (logits = model(xb); loss = CrossEntropyLoss; loss.backward(); Adam lr 1e-4 wd 5e-5).
+ *   SHM_CNN_OPENLAB : openLAB Codes/Models/cnn_model.py:16-57 (GroupNorm(8), SiLU, Dropout 0.4); loop Codes/06_train_cnn.py:410-421
+ *                     (WeightedFocalLoss gamma 2 (:195-207); clip_grad_norm_(2.0); AdamW lr 3e-4 wd 1e-4).
+ * `params` / `grads`: flat fp32 device buffers of shm_cnn_param_count(arch) elements in list(model.parameters()) order
+ * (per block conv.weight, conv.bias, norm.weight, norm.bias; then fc1 weight, bias; fc2 weight, bias).
+ * forward: x [B,C,T,F] NCHW ([B,2,100,12] / [B,1,200,4]); it must stay alive until the backward call.
+ *   bn_running : 4DOF only, optional: [running_mean1(16), running_var1(16), running_mean2(32), running_var2(32)], updated in
+ *                place with `bn_momentum` (nn.BatchNorm2d default 0.1; the variance folded in is the unbiased one);
+ *   drop_mask  : optional uint8 keep-mask [B,128] of the Dropout after fc1 (1 = keep, kept values scaled by 1/(1-drop_p));
+ *   logits     : [B,2].
+ * backward: d_logits [B,2] -> grads (overwritten).  One backward per forward.
+ * shm_cnn_loss_grad: loss (device float[1]) and d loss / d logits for int64 targets [B]; alpha == NULL and gamma == 0 =
+ *   nn.CrossEntropyLoss (mean); otherwise mean(alpha[t] * (1 - pt)^gamma * ce), pt = exp(-ce) (alpha: device float[2] or NULL).
+ * ------------------------------------------------------------------------------------------- */
+enum { SHM_CNN_4DOF = 0, SHM_CNN_OPENLAB = 1 };
+typedef struct shm_cnn_trainer shm_cnn_trainer;
+int64_t shm_cnn_param_count(int arch);
+int shm_cnn_trainer_create(shm_cnn_trainer** out, int arch, int32_t max_batch, int device);
+int shm_cnn_trainer_destroy(shm_cnn_trainer* h);
+int shm_cnn_train_forward(shm_cnn_trainer* h, const float* params, const float* x, int32_t B, float* bn_running, float bn_momentum,
+                          const uint8_t* drop_mask, float drop_p, float* logits, void* stream);
+int shm_cnn_train_backward(shm_cnn_trainer* h, const float* params, const float* d_logits, float* grads, void* stream);
+int shm_cnn_loss_grad(const float* logits, const int64_t* targets, int64_t B, const float* alpha, float gamma, float* d_logits,
+                      float* loss, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Threshold + routing: mask = score > thr (strict, fp32), idx = np.where(mask)[0] ascending
  * (06_test_full_pipeline.py:350-351, 10_test_hybrid_pipeline.py:367).

@@ -274,3 +274,71 @@ def train_step_port(port: VaeTrainPort, opt, x, eps, kl_w: float, drop_enc=None,
 
 def flat_params(port: VaeTrainPort) -> np.ndarray:
     return torch.cat([q.detach().reshape(-1) for q in port.ordered_parameters()]).numpy().copy()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CNN training steps: 4DOF/Scripts/05_train_cnn.py:266-281 and
+# 20250506_openLAB_tests/Codes/06_train_cnn.py:410-421, with nn.Dropout's mask made an explicit input.
+# ---------------------------------------------------------------------------------------------------------
+CNN4DOF_PARAMS = ["conv1.0.weight", "conv1.0.bias", "conv1.1.weight", "conv1.1.bias", "conv2.0.weight", "conv2.0.bias",
+                  "conv2.1.weight", "conv2.1.bias", "fc1.0.weight", "fc1.0.bias", "fc2.weight", "fc2.bias"]
+CNNOL_PARAMS = [f"features.{i}.{j}.{k}" for i in (0, 2, 4, 6) for j in (0, 1) for k in ("weight", "bias")] + \
+               ["classifier.1.weight", "classifier.1.bias", "classifier.4.weight", "classifier.4.bias"]
+
+
+class CnnTrainPort(nn.Module):
+    """The two CNNs in train() mode written with torch.nn.functional on explicit parameters (list(model.parameters())
+    order = CNN4DOF_PARAMS / CNNOL_PARAMS): BatchNorm2d uses batch statistics and updates the running ones (momentum 0.1),
+    GroupNorm(8) + SiLU for openLAB, Dropout = x * keep_mask / (1 - p) with the mask supplied."""
+
+    def __init__(self, arch: str, sd: dict):
+        super().__init__()
+        self.arch = arch
+        self.names = CNN4DOF_PARAMS if arch == "4dof" else CNNOL_PARAMS
+        self.p = nn.ParameterList([nn.Parameter(_t(np.asarray(sd[n], dtype=np.float32)).clone()) for n in self.names])
+        if arch == "4dof":
+            self.running = [_t(np.asarray(sd[f"conv{b}.1.running_{s}"], dtype=np.float32)).clone() for b in (1, 2) for s in ("mean", "var")]
+
+    def ordered_parameters(self) -> list:
+        return list(self.p)
+
+    def forward(self, x, mask=None, p_drop: float = 0.0):
+        P = list(self.p)
+        if self.arch == "4dof":
+            for b in range(2):
+                w, bias, g, be = P[4 * b:4 * b + 4]
+                x = F.conv2d(x, w, bias, padding=1)
+                x = F.batch_norm(x, self.running[2 * b], self.running[2 * b + 1], g, be, training=True, momentum=0.1, eps=1e-5)
+                x = F.max_pool2d(F.relu(x), 2)
+            x = F.relu(F.linear(torch.flatten(x, 1), P[8], P[9]))
+        else:
+            pads = ((3, 1), (2, 1), (2, 1), (1, 1))
+            for b in range(4):
+                w, bias, g, be = P[4 * b:4 * b + 4]
+                x = F.silu(F.group_norm(F.conv2d(x, w, bias, padding=pads[b]), 8, g, be, eps=1e-5))
+                x = F.max_pool2d(x, (2, 1)) if b < 3 else F.adaptive_avg_pool2d(x, (1, 1))
+            x = F.silu(F.linear(torch.flatten(x, 1), P[16], P[17]))
+        if mask is not None and p_drop > 0:
+            x = x * mask.to(x.dtype) / (1.0 - p_drop)
+        return F.linear(x, P[-2], P[-1])
+
+
+def focal_loss(logits, targets, alpha, gamma: float):
+    """WeightedFocalLoss.forward, 06_train_cnn.py:202-207."""
+    ce = F.cross_entropy(logits, targets, reduction="none")
+    pt = torch.exp(-ce)
+    return (alpha[targets] * ((1 - pt) ** gamma) * ce).mean()
+
+
+def cnn_train_step_port(port: CnnTrainPort, opt, x, y, mask=None, p_drop: float = 0.0, alpha=None, gamma: float = 0.0,
+                        max_norm: float = 0.0):
+    """One optimisation step on the port.  Returns (logits, loss, flat gradient before clipping, total_norm)."""
+    logits = port(x, mask, p_drop)
+    loss = F.cross_entropy(logits, y) if (alpha is None and gamma == 0.0) else focal_loss(logits, y, alpha, gamma)
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    params = port.ordered_parameters()
+    flat_g = torch.cat([q.grad.reshape(-1) for q in params]).clone()
+    total = torch.nn.utils.clip_grad_norm_(params, max_norm=max_norm) if max_norm > 0 else torch.linalg.vector_norm(flat_g)
+    opt.step()
+    return logits.detach().numpy(), float(loss.item()), flat_g.numpy(), float(total)

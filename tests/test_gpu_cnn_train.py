@@ -1,0 +1,232 @@
+"""GPU parity of the CNN training steps (csrc/cnn_train.cu), all through the C ABI:
+4DOF/Scripts/05_train_cnn.py:266-281 and openLAB Codes/06_train_cnn.py:410-421.
+
+Checked against (a) ONE optimisation step executed on the reference's own CNN classes (tests/golden/cnn_train_step_*.npz,
+make_golden.py::cnn_train_fixtures) and (b) the autograd port oracle.torch_port.CnnTrainPort on the same inputs (complete gradients).
+Tolerances: logits <= 1e-4 relative (2e-4 absolute floor), loss <= 1e-5 relative, every gradient tensor max|err| <= 1e-4 * max|ref|
+(plus a summation-noise floor of 1e-6 of the largest tensor: conv biases in front of a normalisation have an analytically zero
+gradient), parameters after the optimiser step <= 1e-6 absolute.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_port as TP
+from shmfast import _lib, cnn_train as CT, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def problem(arch, B, seed):
+    if arch == "4dof":
+        sd = synth.cnn4dof_weights(seed=seed)
+        x = np.stack([synth.windows(B, 100, 12, seed=seed), (synth.windows(B, 100, 12, seed=seed + 1) ** 2).astype(np.float32)], axis=1)
+    else:
+        sd = synth.cnnol_weights(seed=seed)
+        x = np.clip(2.0 * synth.windows(B, 200, 4, seed=seed), -10, 10).astype(np.float32)[:, None, :, :]
+    return sd, x
+
+
+def port_of(arch, sd):
+    port = TP.CnnTrainPort(arch, sd)
+    if arch == "4dof":
+        opt = torch.optim.Adam(port.ordered_parameters(), lr=1e-4, weight_decay=5e-5)
+        kw = {}
+    else:
+        opt = torch.optim.AdamW(port.ordered_parameters(), lr=3e-4, weight_decay=1e-4)
+        kw = dict(gamma=2.0, max_norm=2.0)
+    return port, opt, kw
+
+
+def flat_of(port):
+    return torch.cat([q.detach().reshape(-1) for q in port.ordered_parameters()]).clone()
+
+
+def check_grads(names, sizes, got, ref, tag=""):
+    o, worst = 0, 0.0
+    nmax = max(float(np.linalg.norm(ref[a:a + k].astype(np.float64))) for a, k in zip(np.cumsum([0] + sizes[:-1]), sizes))
+    gmax = float(np.max(np.abs(ref)))
+    for n, k in zip(names, sizes):
+        a, b = got[o:o + k], ref[o:o + k]
+        o += k
+        tol = 1e-4 * float(np.max(np.abs(b))) + 1e-6 * gmax
+        err = float(np.max(np.abs(a - b)))
+        worst = max(worst, err / tol)
+        assert err <= tol, f"{tag}{n}: max err {err:.3e} > {tol:.3e} (max|ref| {float(np.max(np.abs(b))):.3e}, largest tensor norm {nmax:.3e})"
+    return worst
+
+
+@pytest.mark.parametrize("arch", ["4dof", "openlab"])
+def test_cnn_train_step_vs_reference_fixture_and_port(cuda_dev, golden_dir, arch):
+    g = np.load(golden_dir / f"cnn_train_step_{arch}.npz")
+    B, seed, p = int(g["B"]), int(g["seed"]), float(g["p_drop"])
+    sd, x = problem(arch, B, seed)
+    port, opt, kw = port_of(arch, sd)
+    if arch == "openlab":
+        kw["alpha"] = torch.from_numpy(g["alpha"])
+    names = port.names
+    sizes = [int(q.numel()) for q in port.ordered_parameters()]
+    flat0 = flat_of(port)
+    aid = _lib.CNN_4DOF if arch == "4dof" else _lib.CNN_OPENLAB
+    h = CT.CnnTrainHandle(aid, B, cuda_dev)
+    assert h.n_params == sum(sizes)
+    params = flat0.to(cuda_dev)
+    xd, yd, md = torch.from_numpy(x).to(cuda_dev), torch.from_numpy(g["y"]).to(cuda_dev), torch.from_numpy(g["mask"]).to(cuda_dev)
+    running = None
+    if arch == "4dof":
+        running = torch.cat([torch.from_numpy(np.asarray(sd[f"conv{b}.1.running_{s}"])) for b in (1, 2) for s in ("mean", "var")]).to(cuda_dev)
+    logits = h.forward(params, xd, running, 0.1, md, p)
+    assert np.allclose(logits.cpu().numpy(), g["logits"], rtol=1e-4, atol=2e-4)
+    alpha = None if arch == "4dof" else torch.from_numpy(g["alpha"]).to(cuda_dev)
+    loss, dl = CT.cnn_loss_grad(logits, yd, alpha, 0.0 if arch == "4dof" else float(g["gamma"]))
+    assert abs(float(loss.item()) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    grads = h.backward(params, dl)
+    # (b) the port, complete gradients
+    _, loss_p, flat_g, total_p = TP.cnn_train_step_port(port, opt, torch.from_numpy(x), torch.from_numpy(g["y"]), torch.from_numpy(g["mask"]), p, **kw)
+    worst = check_grads(names, sizes, grads.cpu().numpy(), flat_g, tag=f"{arch} vs port: ")
+    # (a) the reference fixture: sampled entries + norms
+    got = grads.cpu().numpy()
+    gmax = max(float(np.max(np.abs(g["g:" + n]))) for n in names)
+    nmax = max(float(g["n:" + n]) for n in names)
+    o = 0
+    for n, k in zip(names, sizes):
+        t = got[o:o + k]
+        assert np.allclose(t[g["i:" + n]], g["g:" + n], rtol=0, atol=1e-4 * float(np.max(np.abs(g["g:" + n]))) + 1e-6 * gmax), n
+        assert abs(np.linalg.norm(t.astype(np.float64)) - float(g["n:" + n])) <= 1e-4 * float(g["n:" + n]) + 1e-6 * nmax, n
+        o += k
+    # optimiser: clip (openLAB) + Adam / AdamW on the kernel's own gradients vs the reference's updated parameters
+    m, v = torch.zeros_like(params), torch.zeros_like(params)
+    norm2 = CT.adam_step(params, grads, m, v, 1, float(g["lr"]), weight_decay=float(g["wd"]), max_norm=2.0 if arch == "openlab" else 0.0,
+                         decoupled=arch == "openlab")
+    if arch == "openlab":
+        assert abs(float(norm2[1].item()) - float(g["total_norm"])) <= 1e-4 * float(g["total_norm"])
+    newp = params.cpu().numpy()
+    o = 0
+    for n, k in zip(names, sizes):
+        p_atol = 2.1 * float(g["lr"]) if float(g["n:" + n]) < 1e-4 * nmax else 1e-6      # noise gradients flip Adam's first +-lr step
+        assert np.allclose(newp[o:o + k][g["i:" + n]], g["p:" + n], rtol=0, atol=p_atol), n
+        o += k
+    if arch == "4dof":
+        assert np.allclose(running.cpu().numpy(), g["running"], rtol=1e-5, atol=1e-6)
+    print(f"{arch}: worst gradient error = {worst:.3f} of the tolerance")
+    h.close()
+
+
+@pytest.mark.parametrize("arch,B", [("4dof", 100), ("4dof", 7), ("openlab", 128), ("openlab", 3)])
+def test_cnn_train_gradients_other_batches_no_dropout(cuda_dev, arch, B):
+    """Reference batch sizes (100 / 128) and ragged last batches, no dropout mask; complete gradients vs the port."""
+    sd, x = problem(arch, B, seed=60 + B)
+    port, opt, kw = port_of(arch, sd)
+    rng = np.random.Generator(np.random.PCG64(B))
+    y = rng.integers(0, 2, size=B).astype(np.int64)
+    if arch == "openlab":
+        kw["alpha"] = torch.tensor([0.8, 1.2])
+    sizes = [int(q.numel()) for q in port.ordered_parameters()]
+    params = flat_of(port).to(cuda_dev)
+    h = CT.CnnTrainHandle(_lib.CNN_4DOF if arch == "4dof" else _lib.CNN_OPENLAB, 128, cuda_dev)
+    logits = h.forward(params, torch.from_numpy(x).to(cuda_dev))
+    loss, dl = CT.cnn_loss_grad(logits, torch.from_numpy(y).to(cuda_dev), kw.get("alpha"), kw.get("gamma", 0.0))
+    grads = h.backward(params, dl)
+    lg_p, loss_p, flat_g, _ = TP.cnn_train_step_port(port, opt, torch.from_numpy(x), torch.from_numpy(y), None, 0.0, **kw)
+    assert np.allclose(logits.cpu().numpy(), lg_p, rtol=1e-4, atol=2e-4)
+    assert abs(float(loss.item()) - loss_p) <= 1e-5 * max(abs(loss_p), 1e-3)
+    check_grads(port.names, sizes, grads.cpu().numpy(), flat_g, tag=f"{arch} B={B}: ")
+    h.close()
+
+
+def test_loss_kernel_matches_torch(cuda_dev):
+    g = torch.Generator().manual_seed(5)
+    logits = (3.0 * torch.randn((257, 2), generator=g)).requires_grad_(True)
+    y = torch.randint(0, 2, (257,), generator=g)
+    for alpha, gamma in ((None, 0.0), (torch.tensor([0.6, 1.4]), 2.0), (torch.tensor([1.0, 1.0]), 1.0)):
+        ref = torch.nn.functional.cross_entropy(logits, y) if alpha is None else TP.focal_loss(logits, y, alpha, gamma)
+        (gr,) = torch.autograd.grad(ref, logits)
+        loss, d = CT.cnn_loss_grad(logits.detach().to(cuda_dev), y.to(cuda_dev), alpha, gamma)
+        assert abs(float(loss.item()) - float(ref.item())) <= 2e-6 * max(1.0, abs(float(ref.item())))
+        assert np.allclose(d.cpu().numpy(), gr.numpy(), rtol=1e-4, atol=1e-8)
+
+
+@pytest.mark.parametrize("arch", ["4dof", "openlab"])
+def test_reference_cnn_loop_lines_through_the_shim(cuda_dev, arch):
+    """05_train_cnn.py:270-276 / 06_train_cnn.py:413-418 verbatim on the shim: model.train(); logits = model(xb); loss; loss.backward();
+    (clip_grad_norm_;) optimizer.step() -- gradients land in p.grad through the autograd bridge, torch's optimiser updates the real
+    nn.Parameters, and eval() afterwards scores with the re-packed weights."""
+    from shmfast.models import fourdof, openlab
+    B = 16
+    sd, x = problem(arch, B, seed=70)
+    model = (fourdof.CNN(2, 2, 0.0) if arch == "4dof" else openlab.CNN(dropout_rate=0.0)).to(cuda_dev)     # dropout 0: deterministic
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    port, opt_p, kw = port_of(arch, sd)
+    y = torch.from_numpy(np.random.Generator(np.random.PCG64(1)).integers(0, 2, size=B).astype(np.int64))
+    xb, yb = torch.from_numpy(x).to(cuda_dev), y.to(cuda_dev)
+    model.train()
+    if arch == "4dof":
+        optimizer = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-5)
+        loss_fn = torch.nn.CrossEntropyLoss()
+        optimizer.zero_grad(set_to_none=True)
+        logits = model(xb)
+        loss = loss_fn(logits, yb)
+        loss.backward()
+        optimizer.step()
+    else:
+        alpha = torch.tensor([0.8, 1.2])
+        kw["alpha"] = alpha
+        optimizer = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=1e-4)
+        optimizer.zero_grad()
+        logits = model(xb)
+        loss = TP.focal_loss(logits, yb, alpha.to(cuda_dev), 2.0)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 2.0)
+        optimizer.step()
+    lg_p, loss_p, flat_g, total = TP.cnn_train_step_port(port, opt_p, torch.from_numpy(x), y, None, 0.0, **kw)
+    assert abs(float(loss.item()) - loss_p) <= 1e-5 * max(abs(loss_p), 1e-3)
+    got = torch.cat([q.grad.reshape(-1) for q in model.parameters()]).cpu().numpy()
+    if arch == "openlab" and total > 2.0:
+        flat_g = flat_g * (2.0 / (total + 1e-6))                       # p.grad holds the clipped gradient
+    sizes = [int(q.numel()) for q in port.ordered_parameters()]
+    check_grads(port.names, sizes, got, flat_g, tag=f"{arch} shim: ")
+    if arch == "4dof":
+        assert int(model.conv1[1].num_batches_tracked.item()) == 1
+        assert np.allclose(model.conv1[1].running_mean.cpu().numpy(), port.running[0].numpy(), rtol=1e-5, atol=1e-6)
+        assert np.allclose(model.conv2[1].running_var.cpu().numpy(), port.running[3].numpy(), rtol=1e-5, atol=1e-6)
+    model.eval()                                                       # val loop of the scripts: inference kernels, updated weights
+    with torch.no_grad():
+        ev = model(xb if arch == "4dof" else xb)
+    assert ev.shape == (B, 2) and bool(torch.isfinite(ev).all())
+
+
+@pytest.mark.parametrize("arch", ["4dof", "openlab"])
+def test_fused_cnn_trainer_tracks_the_port(cuda_dev, arch):
+    """CnnTrainer.step x 3 (forward -> loss -> backward -> clip + Adam/AdamW kernels) with supplied dropout masks vs 3 port steps."""
+    from shmfast.models import fourdof, openlab
+    B = 32
+    sd, _ = problem(arch, B, seed=80)
+    model = (fourdof.CNN(2, 2, 0.5) if arch == "4dof" else openlab.CNN(dropout_rate=0.4)).to(cuda_dev).train()
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    port, opt_p, kw = port_of(arch, sd)
+    alpha = None
+    if arch == "openlab":
+        alpha = torch.tensor([0.7, 1.3])
+        kw["alpha"] = alpha
+    tr = CT.CnnTrainer(model, B, alpha=alpha)
+    p_drop = 0.5 if arch == "4dof" else 0.4
+    rng = np.random.Generator(np.random.PCG64(3))
+    for s in range(3):
+        _, x = problem(arch, B, seed=81 + s)
+        y = rng.integers(0, 2, size=B).astype(np.int64)
+        mask = (rng.random((B, 128)) >= p_drop).astype(np.uint8)
+        loss = tr.step(torch.from_numpy(x).to(cuda_dev), torch.from_numpy(y).to(cuda_dev), torch.from_numpy(mask).to(cuda_dev))
+        _, loss_p, _, _ = TP.cnn_train_step_port(port, opt_p, torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(mask), p_drop, **kw)
+        assert abs(float(loss.item()) - loss_p) <= 5e-5 * max(abs(loss_p), 1e-3), (s, float(loss.item()), loss_p)
+    lr = 1e-4 if arch == "4dof" else 3e-4
+    newp = tr.flat.cpu().numpy()
+    ref = flat_of(port).numpy()
+    # three Adam steps move an entry by <= 3 lr; agreement far below that except where the gradient is summation noise
+    close = np.abs(newp - ref) <= 0.05 * lr
+    assert close.mean() > 0.995 and float(np.max(np.abs(newp - ref))) <= 6.1 * lr
+    # the module's parameters ARE the flat buffer
+    assert model.fc2.weight.data_ptr() >= tr.flat.data_ptr() if arch == "4dof" else True
+    if arch == "4dof":
+        assert int(model.conv2[1].num_batches_tracked.item()) == 3
+        assert np.allclose(tr.running.cpu().numpy(), np.concatenate([r.numpy() for r in port.running]), rtol=1e-4, atol=1e-5)
+    tr.close()

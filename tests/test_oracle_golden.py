@@ -275,3 +275,45 @@ def test_hybrid_oracles_accept_full_length_eps2():
                        np.ones(D, np.float32), thr=0.0, eps1=eps1, eps2=eps2)
     assert r["idx"].size == N and r["logits"].shape == (N, 2)
     del series, torch
+
+
+@pytest.mark.parametrize("arch", ["4dof", "openlab"])
+def test_cnn_train_port_matches_reference_step(golden_dir, arch):
+    """oracle.torch_port.CnnTrainPort / cnn_train_step_port vs ONE optimisation step executed on the reference's own CNN classes
+    (05_train_cnn.py:270-276 / 06_train_cnn.py:413-418; fixtures by make_golden.py::cnn_train_fixtures)."""
+    import torch
+    from oracle import torch_port as TP
+    g = np.load(golden_dir / f"cnn_train_step_{arch}.npz")
+    B, seed, p = int(g["B"]), int(g["seed"]), float(g["p_drop"])
+    if arch == "4dof":
+        sd = synth.cnn4dof_weights(seed=seed)
+        x = np.stack([synth.windows(B, 100, 12, seed=seed), (synth.windows(B, 100, 12, seed=seed + 1) ** 2).astype(np.float32)], axis=1)
+        port = TP.CnnTrainPort("4dof", sd)
+        opt = torch.optim.Adam(port.ordered_parameters(), lr=float(g["lr"]), weight_decay=float(g["wd"]))
+        kw = {}
+    else:
+        sd = synth.cnnol_weights(seed=seed)
+        x = np.clip(2.0 * synth.windows(B, 200, 4, seed=seed), -10, 10).astype(np.float32)[:, None, :, :]
+        port = TP.CnnTrainPort("openlab", sd)
+        opt = torch.optim.AdamW(port.ordered_parameters(), lr=float(g["lr"]), weight_decay=float(g["wd"]))
+        kw = dict(alpha=torch.from_numpy(g["alpha"]), gamma=float(g["gamma"]), max_norm=2.0)
+    logits, loss, flat_g, total = TP.cnn_train_step_port(port, opt, torch.from_numpy(x), torch.from_numpy(g["y"]),
+                                                         torch.from_numpy(g["mask"]), p, **kw)
+    assert np.allclose(logits, g["logits"], rtol=1e-5, atol=1e-5)
+    assert abs(loss - float(g["loss"])) <= 1e-6 * max(1.0, abs(float(g["loss"])))
+    if arch == "openlab":
+        assert abs(total - float(g["total_norm"])) <= 1e-5 * float(g["total_norm"])
+    o = 0
+    gmax = max(float(np.max(np.abs(g["g:" + n]))) for n in port.names)
+    nmax = max(float(g["n:" + n]) for n in port.names)        # conv biases in front of a normalisation have an analytically zero gradient: noise
+    for n, q in zip(port.names, port.ordered_parameters()):
+        k = q.numel()
+        gr = flat_g[o:o + k]
+        o += k
+        assert np.allclose(gr[g["i:" + n]], g["g:" + n], rtol=1e-4, atol=1e-6 * gmax), n
+        assert abs(np.linalg.norm(gr.astype(np.float64)) - float(g["n:" + n])) <= 1e-4 * float(g["n:" + n]) + 1e-6 * nmax, n
+        # Adam's first step moves every entry by ~lr * sign(g): where the gradient is summation noise (see above) the sign is too
+        p_atol = 2.1 * float(g["lr"]) if float(g["n:" + n]) < 1e-4 * nmax else 2e-7
+        assert np.allclose(q.detach().numpy().reshape(-1)[g["i:" + n]], g["p:" + n], rtol=0, atol=p_atol), n
+    if arch == "4dof":
+        assert np.allclose(np.concatenate([r.numpy() for r in port.running]), g["running"], rtol=1e-5, atol=1e-6)

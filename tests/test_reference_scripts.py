@@ -106,9 +106,20 @@ def test_oracle_equals_unmodified_06_main_on_cpu(golden_dir, tmp_path):
 # ------------------------------------------------------------------------------------------------------------
 # GPU: reference Models (cuDNN) vs the shmfast stubs, same script, same seed
 # ------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def fp32_cudnn():
+    """PyTorch lets cuDNN use TF32 tensor cores for LSTM / conv by default (torch.backends.cudnn.allow_tf32 = True): on B200
+    the reference then deviates from ITS OWN fp32 result by 8.5e-5 (scores) and 1.2e-3 (p_struct) on this fixture
+    (profiles/r02_ref06_diag.log).  The 1e-4 contract is stated for fp32 accumulate, so the reference runs in true fp32 here."""
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = prev
+
+
 @needs_ref
 @pytest.mark.gpu
-def test_06_main_reference_models_vs_shmfast_stubs(cuda_dev, golden_dir, tmp_path):
+def test_06_main_reference_models_vs_shmfast_stubs(cuda_dev, golden_dir, tmp_path, fp32_cudnn):
     """The unmodified 06_test_full_pipeline.main() on the repo's 4040 real test windows with reference-trained weights."""
     g, vae_sd, cnn_sd = _trained(golden_dir)
     thr = float(g["thr"])
@@ -141,7 +152,7 @@ def test_06_main_reference_models_vs_shmfast_stubs(cuda_dev, golden_dir, tmp_pat
 
 @needs_ref
 @pytest.mark.gpu
-def test_04_full_mse_scores_batched_reference_vs_stub(cuda_dev, golden_dir, tmp_path):
+def test_04_full_mse_scores_batched_reference_vs_stub(cuda_dev, golden_dir, tmp_path, fp32_cudnn):
     """`full_mse_scores_batched` (04_vae_thresholding.py:113-124) imported from the unmodified script, P99 threshold rule (:283)."""
     g, vae_sd, cnn_sd = _trained(golden_dir)
     Z = g["Z"]
@@ -162,7 +173,7 @@ def test_04_full_mse_scores_batched_reference_vs_stub(cuda_dev, golden_dir, tmp_
 
 @needs_ref
 @pytest.mark.gpu
-def test_10_openlab_functions_reference_vs_stub(cuda_dev, golden_dir, tmp_path):
+def test_10_openlab_functions_reference_vs_stub(cuda_dev, golden_dir, tmp_path, fp32_cudnn):
     """`recon_mse_per_window` (10_test_hybrid_pipeline.py:240-251), `standardize` (:233-237) and `stage2_predict_cnn` (:265-302)
     imported from the unmodified script, on real openLAB windows (NaN-bearing X_raw rows included)."""
     g = np.load(golden_dir / "openlab_real_windows.npz")
