@@ -789,6 +789,88 @@ def measure_train(ctx, a, B, steps, warmup, e2e=True, cpu=True, sample_clocks=Tr
     return line
 
 
+# ----------------------------------------------------------------------------------------------
+# CNN training steps: 4DOF/Scripts/05_train_cnn.py:266-281 (batch 100, CE, Adam) and
+# openLAB Codes/06_train_cnn.py:410-421 (batch 128, weighted focal loss, clip 2.0, AdamW); fp32 FMA implicit-GEMM convolutions.
+# ----------------------------------------------------------------------------------------------
+CNN_TRAIN_FLOP = {"4dof": 3 * 4_070_912, "openlab": 3 * 133_851_648}       # forward + ~2x backward per window
+
+
+def measure_cnn_train(ctx, arch: str, steps: int, warmup: int, incumbent: bool = True):
+    from shmfast import cnn_train as CT, synth
+    from shmfast.models import fourdof, openlab
+    dev = ctx.dev
+    B = 100 if arch == "4dof" else 128
+    if arch == "4dof":
+        model = fourdof.CNN(2, 2, 0.5)
+        sd = synth.cnn4dof_weights(seed=0)
+        xs = [np.stack([synth.windows(B, 100, 12, seed=10 + i), synth.windows(B, 100, 12, seed=20 + i) ** 2], axis=1).astype(np.float32) for i in range(4)]
+        alpha = None
+    else:
+        model = openlab.CNN(dropout_rate=0.4)
+        sd = synth.cnnol_weights(seed=0)
+        xs = [np.clip(2.0 * synth.windows(B, 200, 4, seed=10 + i), -10, 10).astype(np.float32)[:, None] for i in range(4)]
+        alpha = torch.tensor([0.8, 1.2])
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    model = model.to(dev).train()
+    tr = CT.CnnTrainer(model, B, alpha=alpha)
+    xd = [torch.from_numpy(x).to(dev) for x in xs]
+    yd = [torch.randint(0, 2, (B,), device=dev) for _ in xs]
+    for i in range(max(1, warmup)):
+        tr.step(xd[i % 4], yd[i % 4])
+    torch.cuda.synchronize()
+    total_ms, _ = ctx.timed(lambda i: tr.step(xd[i % 4], yd[i % 4]), steps, False)
+    ms = total_ms / steps
+    achieved = CNN_TRAIN_FLOP[arch] * B / (ms / 1e3) / 1e12
+    out = {"value": ctx.sum(float(B * steps)) / (total_ms / 1e3), "unit": "windows/s", "ms_per_step": ms, "steps": steps, "batch_per_gpu": B,
+           "config": {"workload": f"{arch}_cnn_train", "loss": "CrossEntropy" if arch == "4dof" else "weighted focal (gamma 2)",
+                      "optimizer": "Adam lr 1e-4 wd 5e-5" if arch == "4dof" else "clip 2.0 + AdamW lr 3e-4 wd 1e-4",
+                      "parallelism": f"dp{ctx.world}, one NCCL all-reduce of the flat gradient per step"},
+           "roofline": {"bound": "fp32", "achieved": achieved, "peak": FP32_PEAK_TF, "unit": "TFLOP/s", "frac": achieved / FP32_PEAK_TF,
+                        "algorithmic_flop_per_window": CNN_TRAIN_FLOP[arch]}}
+    tr.close()
+    if incumbent and ctx.rank == 0 and ctx.world == 1:
+        try:
+            from oracle import ref_driver as R
+            from oracle import torch_port as TP
+            if R.ref_root() is not None:
+                _, Cn = R.reference_models("4dof" if arch == "4dof" else "openlab")
+                ref = Cn(input_channels=2, num_classes=2, dropout_rate=0.5) if arch == "4dof" else Cn(dropout_rate=0.4)
+                ref.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+                ref = ref.to(dev).train()
+                if arch == "4dof":
+                    opt = torch.optim.Adam(ref.parameters(), lr=1e-4, weight_decay=5e-5)
+                    lossf = torch.nn.CrossEntropyLoss()
+                else:
+                    opt = torch.optim.AdamW(ref.parameters(), lr=3e-4, weight_decay=1e-4)
+                    al = alpha.to(dev)
+                    lossf = lambda lg, y: TP.focal_loss(lg, y, al, 2.0)
+
+                def ref_step(i):
+                    opt.zero_grad()
+                    loss = lossf(ref(xd[i % 4]), yd[i % 4])
+                    loss.backward()
+                    if arch != "4dof":
+                        torch.nn.utils.clip_grad_norm_(ref.parameters(), 2.0)
+                    opt.step()
+
+                for i in range(3):
+                    ref_step(i)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(10):
+                    ref_step(i)
+                e1.record()
+                torch.cuda.synchronize()
+                rms = e0.elapsed_time(e1) / 10
+                out["torch_cuda_baseline"] = {"value": B / (rms / 1e3), "unit": "windows/s", "ms_per_step": rms,
+                                              "kind": "reference CNN class on torch CUDA kernels (cuDNN conv fwd+bwd, torch optimiser), batch resident"}
+        except Exception as e:
+            out["torch_cuda_baseline"] = {"unavailable": repr(e)[:200]}
+    return out
+
+
 TRAIN_LAUNCHES_PER_STEP = 47        # profiles/r01_train_launches_v2.csv: 141 libshmfast launches in 3 steps
 
 
@@ -919,7 +1001,7 @@ def measure_membound(ctx):
     b = N2 * 200 * 4 * 4 + ser2.numel() * 4
     out["gather_openlab_stride20"] = {"gbs": b / ms / 1e6, "frac": b / ms / 1e6 / peak, "ms": ms, "bytes": b}
     del buf2, ser2
-    M = 1 << 26
+    M = 1 << 27
     score = torch.rand(M, device=dev)
     for frac, name in ((0.01, "compact_1pct"), (0.47, "compact_47pct")):
         ms = timed(lambda: ops.compact(score, 1.0 - frac))
@@ -928,7 +1010,7 @@ def measure_membound(ctx):
     ms = timed(lambda: ops.percentile(score, 99.0))
     out["percentile_p99"] = {"gbs": M * 4 / ms / 1e6, "frac": M * 4 / ms / 1e6 / peak, "ms": ms, "bytes": M * 4}
     out["peak_gbs"] = peak
-    out["note"] = "algorithmic bytes (unique bytes read + bytes written) / CUDA-event time; 2^26 scores, 2^19 / 2^20 windows"
+    out["note"] = "algorithmic bytes (unique bytes read + bytes written) / CUDA-event time; 2^27 scores, 2^19 / 2^20 windows"
     return out
 
 
@@ -1036,6 +1118,8 @@ def secondary(ctx, a):
     leg("4dof_train_b256", lambda: measure_train(ctx, a, 256, 40, 3, e2e=False, cpu=False, sample_clocks=False, full=False))
     if ctx.rank == 0 and ctx.world == 1:
         leg("4dof_train_torch_cuda_baseline", lambda: incumbent_train(ctx))
+    leg("4dof_cnn_train_b100", lambda: measure_cnn_train(ctx, "4dof", 30, 3))
+    leg("openlab_cnn_train_b128", lambda: measure_cnn_train(ctx, "openlab", 20, 3))
     leg("shard_check", lambda: shard_check(ctx))
     if ctx.rank == 0 and ctx.world == 1:
         leg("membound", lambda: measure_membound(ctx))

@@ -336,6 +336,44 @@ def test_percentile_bit_exact(cuda_dev, N, q):
     assert got == float(np.percentile(s, q))
 
 
+@pytest.mark.parametrize("kind", ["constant", "sorted", "reversed", "two_values", "periodic_adversarial", "with_inf", "large", "unaligned"])
+@pytest.mark.parametrize("q", [99.0, 50.0, 3.7])
+def test_percentile_single_pass_edge_cases(cuda_dev, kind, q):
+    """The one-read front end (sample bracket -> filter -> select among candidates) and its device-side fallback stay bit-exact:
+    ties, monotone inputs, a periodic input built so that the strided sample sees only the large values (bracket misses both
+    ranks -> full-array select), infinities, 2^23 scores, and a view that is not 16-byte aligned."""
+    rng = np.random.Generator(np.random.PCG64(17))
+    N = 1 << 19
+    if kind == "constant":
+        s = np.full(N, 1.25, np.float32)
+    elif kind == "sorted":
+        s = np.sort(rng.standard_normal(N).astype(np.float32) ** 2)
+    elif kind == "reversed":
+        s = np.sort(rng.standard_normal(N).astype(np.float32) ** 2)[::-1].copy()
+    elif kind == "two_values":
+        s = np.where(rng.random(N) < 0.3, 0.5, 2.0).astype(np.float32)
+    elif kind == "periodic_adversarial":
+        s = rng.random(N).astype(np.float32)
+        s[:: N // 16384] += 100.0                                  # exactly the positions the strided sample reads
+    elif kind == "with_inf":
+        s = rng.standard_normal(N).astype(np.float32) ** 2
+        s[rng.integers(0, N, 4000)] = np.inf
+        s[rng.integers(0, N, 4000)] = -np.inf
+    elif kind == "large":
+        N = 1 << 23
+        s = np.exp(rng.standard_normal(N)).astype(np.float32)
+    else:
+        s = (rng.standard_normal(N + 1).astype(np.float32) ** 2)
+    if kind == "unaligned":
+        d = to_dev(s, cuda_dev)[1:]
+        s = s[1:]
+    else:
+        d = to_dev(s, cuda_dev)
+    got = float(ops.percentile(d, q).item())
+    ref = float(np.percentile(s, q))
+    assert got == ref or (np.isnan(got) and np.isnan(ref)), (kind, q, got, ref)
+
+
 def test_full_size_properties(cuda_dev):
     """BASELINE-size run (2^18 windows here, same code path as 2^20): size-independent properties --
     determinism, permutation equivariance through the gather list, series-gather == materialised."""

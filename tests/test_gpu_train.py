@@ -217,9 +217,13 @@ def test_ddp_two_gpus_matches_single(tmp_path):
     script = tmp_path / "ddp_worker.py"
     script.write_text(DDP_WORKER)
     env = dict(os.environ, SHM_PKG=str(root / "hybrid-vae-cnn-for-shm_b200"), SHM_ROOT=str(root), OUT=str(tmp_path))
+    import socket
     for world in (1, 2):
+        with socket.socket() as sk:                       # a free rendezvous port (concurrent test runs must not collide)
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
-                            "127.0.0.1", "--master-port", "29541", str(script)], env=env, capture_output=True, text=True, timeout=600)
+                            "127.0.0.1", "--master-port", str(port), str(script)], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout + r.stderr
     a, b = np.load(tmp_path / "flat_w1.npy"), np.load(tmp_path / "flat_w2.npy")
     assert np.mean(np.abs(a - b) <= 2e-5) > 0.99 and np.max(np.abs(a - b)) <= 3.1e-3
