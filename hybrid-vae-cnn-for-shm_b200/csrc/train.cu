@@ -167,16 +167,18 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmArgs g) {
     }
 }
 
-int sgemm(cudaStream_t st, const float* A, long long a_ms, long long a_ks, const float* B, long long b_ks, long long b_ns, float* C,
-          long long ldc, int M, int N, int K, const float* bias1, const float* bias2, bool splitk);
 
+// Forward contractions (activations x weights, O(1) magnitudes) take the fp16 split, backward ones (gradients) the bf16 split;
+// small or oddly shaped ones stay on the fp32 FMA kernel below (sgemm_mode decides).
+static int g_train_tc = 1;          // shm_vae_trainer_set_engine: 0 = all contractions on the fp32 FMA pipe
 static inline int gemm(cudaStream_t st, const float* A, long long a_ms, long long a_ks, const float* B, long long b_ks, long long b_ns,
-                       float* C, long long ldc, int M, int N, int K, const float* bias1, const float* bias2, bool splitk) {
-    return sgemm(st, A, a_ms, a_ks, B, b_ks, b_ns, C, ldc, M, N, K, bias1, bias2, splitk);
+                       float* C, long long ldc, int M, int N, int K, const float* bias1, const float* bias2, bool splitk,
+                       int mode = SHM_GEMM_SIMT) {
+    return sgemm_mode(st, A, a_ms, a_ks, B, b_ks, b_ns, C, ldc, M, N, K, bias1, bias2, splitk, g_train_tc ? mode : SHM_GEMM_SIMT);
 }
 
-int sgemm(cudaStream_t st, const float* A, long long a_ms, long long a_ks, const float* B, long long b_ks, long long b_ns, float* C,
-          long long ldc, int M, int N, int K, const float* bias1, const float* bias2, bool splitk) {
+int sgemm_simt(cudaStream_t st, const float* A, long long a_ms, long long a_ks, const float* B, long long b_ks, long long b_ns, float* C,
+               long long ldc, int M, int N, int K, const float* bias1, const float* bias2, bool splitk) {
     if (M <= 0 || N <= 0 || K <= 0) return SHM_OK;
     GemmArgs g{A, a_ms, a_ks, B, b_ks, b_ns, C, ldc, M, N, K, bias1, bias2, K, splitk ? 1 : 0};
     const bool narrow = N <= 16;
@@ -841,7 +843,7 @@ extern "C" int shm_vae_train_forward(shm_vae_trainer* h, const float* params, co
         const float* in = l == 0 ? ws + h->x_tm : (ws + h->hd[0][l - 1]);
         const int K = l == 0 ? D : H;
         if ((rc = gemm(st, in, K, 1, params + pl.enc_wih[l], 1, K, ws + h->G[0][l], 4 * H, (int)TB, 4 * H, K,
-                       params + pl.enc_bih[l], params + pl.enc_bhh[l], false))) return rc;
+                       params + pl.enc_bih[l], params + pl.enc_bhh[l], false, SHM_GEMM_TC_F16X3))) return rc;
         const bool last = l == L - 1;
         const uint8_t* mk = (!last && h->use_mask) ? h->masks + (size_t)l * mask_layer : nullptr;
         if ((rc = rec_fwd(H, st, h->nsm, params + pl.enc_whh[l], ws + h->G[0][l], (long long)B * 4 * H, ws + h->G[0][l],
@@ -868,7 +870,7 @@ extern "C" int shm_vae_train_forward(shm_vae_trainer* h, const float* params, co
                               ws + h->cs[1][0], last ? nullptr : ws + h->hd[1][0], mk, h->scale, T, B))) return rc;
         } else {
             if ((rc = gemm(st, ws + h->hd[1][l - 1], H, 1, params + pl.dec_wih[l], 1, H, ws + h->G[1][l], 4 * H, (int)TB, 4 * H, H,
-                           params + pl.dec_bih[l], params + pl.dec_bhh[l], false))) return rc;
+                           params + pl.dec_bih[l], params + pl.dec_bhh[l], false, SHM_GEMM_TC_F16X3))) return rc;
             if ((rc = rec_fwd(H, st, h->nsm, params + pl.dec_whh[l], ws + h->G[1][l], (long long)B * 4 * H, ws + h->G[1][l],
                               ws + h->hs[1][l], ws + h->cs[1][l], last ? nullptr : ws + h->hd[1][l], mk, h->scale, T, B))) return rc;
         }
@@ -903,11 +905,11 @@ extern "C" int shm_vae_train_backward(shm_vae_trainer* h, const float* params, c
     swap01_kernel<<<296, 256, 0, st>>>(d_xhat, dx_tm, B, T, D);
     SHM_LAUNCH_CHECK();
     const float* htop = ws + h->hs[1][L - 1] + (size_t)B * H;
-    if ((rc = gemm(st, dx_tm, 1, D, htop, H, 1, grads + pl.out_w, H, D, H, (int)TB, nullptr, nullptr, true))) return rc;
+    if ((rc = gemm(st, dx_tm, 1, D, htop, H, 1, grads + pl.out_w, H, D, H, (int)TB, nullptr, nullptr, true, SHM_GEMM_TC_BF16X3))) return rc;
     if ((rc = colsum(st, dx_tm, nullptr, (int)TB, D, grads + pl.out_b, nullptr))) return rc;
     float* dH = ws + h->dHa;
     float* dH2 = ws + h->dHb;
-    if ((rc = gemm(st, dx_tm, D, 1, params + pl.out_w, H, 1, dH, H, (int)TB, H, D, nullptr, nullptr, false))) return rc;
+    if ((rc = gemm(st, dx_tm, D, 1, params + pl.out_w, H, 1, dH, H, (int)TB, H, D, nullptr, nullptr, false, SHM_GEMM_TC_BF16X3))) return rc;
     // decoder stack, top down
     for (int l = L - 1; l >= 0; --l) {
         // dH is the gradient w.r.t. this layer's (dropped, if not the top) output sequence
@@ -915,13 +917,13 @@ extern "C" int shm_vae_train_backward(shm_vae_trainer* h, const float* params, c
         float* dG = ws + h->G[1][l];
         if ((rc = rec_bwd(H, st, h->nsm, params + pl.dec_whh[l], dG, ws + h->cs[1][l], dH, mk, h->scale, nullptr,
                           l == 0 ? ws + h->dgsum : nullptr, T, B))) return rc;
-        if ((rc = gemm(st, dG, 1, 4 * H, ws + h->hs[1][l], H, 1, grads + pl.dec_whh[l], H, 4 * H, H, (int)TB, nullptr, nullptr, true)))
+        if ((rc = gemm(st, dG, 1, 4 * H, ws + h->hs[1][l], H, 1, grads + pl.dec_whh[l], H, 4 * H, H, (int)TB, nullptr, nullptr, true, SHM_GEMM_TC_BF16X3)))
             return rc;
         if ((rc = colsum(st, dG, nullptr, (int)TB, 4 * H, grads + pl.dec_bih[l], grads + pl.dec_bhh[l]))) return rc;
         if (l > 0) {
-            if ((rc = gemm(st, dG, 1, 4 * H, ws + h->hd[1][l - 1], H, 1, grads + pl.dec_wih[l], H, 4 * H, H, (int)TB, nullptr, nullptr, true)))
+            if ((rc = gemm(st, dG, 1, 4 * H, ws + h->hd[1][l - 1], H, 1, grads + pl.dec_wih[l], H, 4 * H, H, (int)TB, nullptr, nullptr, true, SHM_GEMM_TC_BF16X3)))
                 return rc;
-            if ((rc = gemm(st, dG, 4 * H, 1, params + pl.dec_wih[l], H, 1, dH2, H, (int)TB, H, 4 * H, nullptr, nullptr, false))) return rc;
+            if ((rc = gemm(st, dG, 4 * H, 1, params + pl.dec_wih[l], H, 1, dH2, H, (int)TB, H, 4 * H, nullptr, nullptr, false, SHM_GEMM_TC_BF16X3))) return rc;
             float* t = dH; dH = dH2; dH2 = t;
         } else {
             if ((rc = gemm(st, ws + h->dgsum, 1, 4 * H, ws + h->h0, H, 1, grads + pl.dec_wih[0], H, 4 * H, H, B, nullptr, nullptr, true)))
@@ -955,13 +957,13 @@ extern "C" int shm_vae_train_backward(shm_vae_trainer* h, const float* params, c
         float* dG = ws + h->G[0][l];
         if ((rc = rec_bwd(H, st, h->nsm, params + pl.enc_whh[l], dG, ws + h->cs[0][l], dHin, mk, h->scale,
                           l == L - 1 ? ws + h->dhn : nullptr, nullptr, T, B))) return rc;
-        if ((rc = gemm(st, dG, 1, 4 * H, ws + h->hs[0][l], H, 1, grads + pl.enc_whh[l], H, 4 * H, H, (int)TB, nullptr, nullptr, true)))
+        if ((rc = gemm(st, dG, 1, 4 * H, ws + h->hs[0][l], H, 1, grads + pl.enc_whh[l], H, 4 * H, H, (int)TB, nullptr, nullptr, true, SHM_GEMM_TC_BF16X3)))
             return rc;
         if ((rc = colsum(st, dG, nullptr, (int)TB, 4 * H, grads + pl.enc_bih[l], grads + pl.enc_bhh[l]))) return rc;
         if (l > 0) {
-            if ((rc = gemm(st, dG, 1, 4 * H, ws + h->hd[0][l - 1], H, 1, grads + pl.enc_wih[l], H, 4 * H, H, (int)TB, nullptr, nullptr, true)))
+            if ((rc = gemm(st, dG, 1, 4 * H, ws + h->hd[0][l - 1], H, 1, grads + pl.enc_wih[l], H, 4 * H, H, (int)TB, nullptr, nullptr, true, SHM_GEMM_TC_BF16X3)))
                 return rc;
-            if ((rc = gemm(st, dG, 4 * H, 1, params + pl.enc_wih[l], H, 1, ws + h->dHa, H, (int)TB, H, 4 * H, nullptr, nullptr, false)))
+            if ((rc = gemm(st, dG, 4 * H, 1, params + pl.enc_wih[l], H, 1, ws + h->dHa, H, (int)TB, H, 4 * H, nullptr, nullptr, false, SHM_GEMM_TC_BF16X3)))
                 return rc;
             dHin = ws + h->dHa;
         } else {
@@ -1022,4 +1024,9 @@ extern "C" int shm_adamw_clip_step(float* params, const float* grads, float* exp
                                    float grad_scale, float* norm2, void* stream) {
     return shm::adam_step((cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, weight_decay, 1, max_norm,
                           grad_scale, norm2);
+}
+
+extern "C" int shm_train_set_tensor_cores(int enable) {
+    shm::g_train_tc = enable ? 1 : 0;
+    return SHM_OK;
 }

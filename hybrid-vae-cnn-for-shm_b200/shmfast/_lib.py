@@ -13,6 +13,7 @@ SHM_MAX_L = 2
 
 ENGINE_AUTO, ENGINE_FP32, ENGINE_TC_BF16X3 = 0, 1, 2
 CNN_4DOF, CNN_OPENLAB = 0, 1
+GEMM_SIMT, GEMM_TC_F16X3, GEMM_TC_BF16X3 = 0, 1, 2
 
 _fp = C.POINTER(C.c_float)
 _vp = C.c_void_p
@@ -94,6 +95,9 @@ SIGNATURES = {
     "shm_vae_elbo_grad": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_float, _vp, _vp, _vp, _vp, _vp]),
     "shm_adam_clip_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_float, C.c_float, C.c_float, _vp, _vp]),
+    "shm_gemm_f32": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _vp,
+                               C.c_int32, C.c_int32, _vp]),
+    "shm_train_set_tensor_cores": (C.c_int, [C.c_int]),
     "shm_adamw_clip_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
                                       C.c_float, C.c_float, C.c_float, _vp, _vp]),
     "shm_cnn_param_count": (C.c_int64, [C.c_int]),

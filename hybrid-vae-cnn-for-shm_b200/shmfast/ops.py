@@ -606,3 +606,16 @@ def hybridol_score(vae: VaeScorer, cnn: CnnOpenLab, src_gate: WindowSource, src_
                                      _ptr(logits), _ptr(prob), _ptr(pred), _ptr(y_pred), _ptr(prob_full), _ptr(ws), ws.numel(),
                                      _stream()), "shm_hybridol_score")
     return out
+
+
+def gemm_f32(A: torch.Tensor, a_ms: int, a_ks: int, B: torch.Tensor, b_ks: int, b_ns: int, M: int, N: int, K: int,
+             bias: Optional[torch.Tensor] = None, splitk: bool = False, mode: int = _lib.GEMM_SIMT) -> torch.Tensor:
+    """C[M,N] = sum_k A[m*a_ms + k*a_ks] * B[k*b_ks + n*b_ns] (+ bias[n]) through shm_gemm_f32: the contraction the training
+    steps run (mode: _lib.GEMM_SIMT / GEMM_TC_F16X3 / GEMM_TC_BF16X3).  A / B are flat float32 CUDA buffers."""
+    lib = _lib.load()
+    A, B = _f32c(A, "A"), _f32c(B, "B")
+    C_ = torch.zeros((M, N), dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        check(lib.shm_gemm_f32(_ptr(A), int(a_ms), int(a_ks), _ptr(B), int(b_ks), int(b_ns), _ptr(C_), N, int(M), int(N), int(K),
+                               _ptr(bias), 1 if splitk else 0, int(mode), _stream()), "shm_gemm_f32")
+    return C_

@@ -213,6 +213,18 @@ int shm_adam_clip_step(float* params, const float* grads, float* exp_avg, float*
                        float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                        float* norm2, void* stream);
 
+/* fp32-grade strided contraction used by the training steps (exposed for tests and callers that want it):
+ *   C[m*ldc + n] (+)= sum_k A[m*a_ms + k*a_ks] * B[k*b_ks + n*b_ns] (+ bias[n]);  splitk != 0: split along K, atomicAdd into C
+ *   (zero C first).  mode SHM_GEMM_SIMT: fp32 FMA pipe.  SHM_GEMM_TC_F16X3 / SHM_GEMM_TC_BF16X3: tcgen05 tensor cores, operands
+ *   split on the fly into 16-bit hi/lo halves, 3 MMA passes, fp32 accumulation in TMEM (fp16 halves: 2^-22 relative with an
+ *   absolute floor of 2^-25, for O(1) activations; bf16 halves: 2^-16 relative over fp32's whole range, for gradients); shapes
+ *   that do not qualify (small, or not float4-loadable along a contiguous dimension) run on the FMA pipe.
+ * shm_train_set_tensor_cores(0) keeps every contraction of the training steps on the FMA pipe (default 1). */
+enum { SHM_GEMM_SIMT = 0, SHM_GEMM_TC_F16X3 = 1, SHM_GEMM_TC_BF16X3 = 2 };
+int shm_gemm_f32(const float* A, int64_t a_ms, int64_t a_ks, const float* B, int64_t b_ks, int64_t b_ns, float* C, int64_t ldc,
+                 int32_t M, int32_t N, int32_t K, const float* bias, int32_t splitk, int32_t mode, void* stream);
+int shm_train_set_tensor_cores(int enable);
+
 /* AdamW twin of shm_adam_clip_step (decoupled weight decay: param *= 1 - lr*weight_decay before the Adam update), the optimiser of
  * openLAB Codes/06_train_cnn.py:395 (AdamW lr 3e-4 wd 1e-4) after clip_grad_norm_(2.0) (:417). */
 int shm_adamw_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t step,
