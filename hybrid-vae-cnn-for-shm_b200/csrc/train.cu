@@ -10,9 +10,11 @@
 //     memory (192 KB at H=128) and the rest in registers -- and the 4 gates of a unit sit in 4 adjacent lanes so
 //     the cell update is a warp-shuffle exchange;
 //   * heads (LayerNorm, mu/logvar, reparameterisation, latent->hidden) are one small kernel per direction.
+#include <cooperative_groups.h>
 #include <new>
 #include "common.cuh"
 #include "gemm.cuh"
+#include "tcgen05.cuh"
 
 namespace shm {
 
@@ -170,7 +172,8 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmArgs g) {
 
 // Forward contractions (activations x weights, O(1) magnitudes) take the fp16 split, backward ones (gradients) the bf16 split;
 // small or oddly shaped ones stay on the fp32 FMA kernel below (sgemm_mode decides).
-static int g_train_tc = 1;          // shm_vae_trainer_set_engine: 0 = all contractions on the fp32 FMA pipe
+static int g_train_tc = 1;
+static int g_rec_cluster = 0;       // H = 128 recurrence on clusters of two CTAs (shm_train_set_tensor_cores bit 1 clear: single-CTA kernels)          // shm_vae_trainer_set_engine: 0 = all contractions on the fp32 FMA pipe
 static inline int gemm(cudaStream_t st, const float* A, long long a_ms, long long a_ks, const float* B, long long b_ks, long long b_ns,
                        float* C, long long ldc, int M, int N, int K, const float* bias1, const float* bias2, bool splitk,
                        int mode = SHM_GEMM_SIMT) {
@@ -256,7 +259,10 @@ template <int H> struct RecCfg {
     static constexpr int MR = 2 * H - MS;              // backward: rows kept in registers
 };
 
-__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
+// ex2.approx + rcp.approx (2 ulp each; the accurate expf / IEEE division / tanhf each carry a slow-path call, visible as
+// CALL.REL + BSSY in the step loop's SASS), far inside the 1e-4 gradient tolerance
+__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_acc(float x) { return fmaf(2.f, sigmoidf_acc(2.f * x), -1.f); }
 
 template <int H, int NW>
 __global__ void __launch_bounds__(2 * H)
@@ -336,13 +342,13 @@ lstm_rec_fwd_kernel(const float* __restrict__ w_hh, const float* gx, long long g
         float* hn = hbuf + ((t + 1) & 1) * NW * H;
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
-            const float v0 = (p == 1) ? tanhf(a0[w]) : sigmoidf_acc(a0[w]);   // p=0: i, p=1: g
+            const float v0 = (p == 1) ? tanhf_acc(a0[w]) : sigmoidf_acc(a0[w]);   // p=0: i, p=1: g
             const float v1 = sigmoidf_acc(a1[w]);                              // p=0: f, p=1: o
             const float o0 = __shfl_xor_sync(0xffffffffu, v0, 1);
             const float o1 = __shfl_xor_sync(0xffffffffu, v1, 1);
             const float gi = p ? o0 : v0, gf = p ? o1 : v1, gg = p ? v0 : o0, go = p ? v1 : o1;
             c[w] = fmaf(gf, c[w], gi * gg);
-            const float h = go * tanhf(c[w]);
+            const float h = go * tanhf_acc(c[w]);
             if (p == 0) hn[w * H + u] = h;
             if (valid[w]) {
                 const size_t tb = (size_t)t * B + (b0 + w);
@@ -423,7 +429,7 @@ lstm_rec_bwd_kernel(const float* __restrict__ w_hh, float* act_dg, const float* 
             const float o0 = __shfl_xor_sync(0xffffffffu, v0c[w], 1);
             const float o1 = __shfl_xor_sync(0xffffffffu, v1c[w], 1);
             const float gi = p ? o0 : v0c[w], gf = p ? o1 : v1c[w], gg = p ? v0c[w] : o0, go = p ? v1c[w] : o1;
-            const float tc = tanhf(ct[w]);
+            const float tc = tanhf_acc(ct[w]);
             const float dct = fmaf(dh * go, 1.f - tc * tc, dc[w]);
             dc[w] = dct * gf;
             float g0, g1;
@@ -471,6 +477,262 @@ lstm_rec_bwd_kernel(const float* __restrict__ w_hh, float* act_dg, const float* 
         for (int w = 0; w < NW; ++w)
             if (valid[w]) { dgsum[(size_t)(b0 + w) * G4 + r0] = gs0[w]; dgsum[(size_t)(b0 + w) * G4 + r1] = gs1[w]; }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Recurrence for H = 128 on a CLUSTER OF TWO CTAs (r02).  profiles/r01_train_rec_v3_raw.csv: the single-CTA kernels above are
+// bound by shared-memory wavefronts -- half of W_hh (128 KB) is re-read from shared memory every step next to the h_{t-1}
+// broadcasts (2.4 k wavefronts per step, LSU data pipe 53 % busy, short-scoreboard stalls dominate, 5.2 k clk per step).  Two SMs
+// together hold all of W_hh in REGISTERS: CTA c owns the four gate rows of units [64c, 64c+64) (256 rows x 128 k = 128 registers per
+// thread), so the only shared-memory traffic left is the h_{t-1} broadcast; each CTA writes its half of h_t into both CTAs'
+// buffers (distributed shared memory) and one cluster barrier per step replaces the block barrier.  Thread j <-> (unit 64c + (j>>2),
+// gate j&3): the 4 gates of a unit sit in 4 adjacent lanes (warp-shuffle cell update).
+// ------------------------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+
+// distributed-shared-memory store that signals the RECEIVER's mbarrier (complete_tx): data and "it has landed" travel together,
+// so a step needs no cluster-wide barrier -- cluster.sync() compiles to MEMBAR.ALL.GPU + CCTL.IVALL, which waits for every
+// outstanding global store of the step (measured: 3.5 us per step with it)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t peer_addr, float v, uint32_t peer_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(peer_addr), "r"(__float_as_uint(v)), "r"(peer_mbar) : "memory");
+}
+// fast gate activations: ex2.approx + rcp.approx (2 ulp each), far inside the 1e-4 gradient tolerance
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, sigmoid_fast(2.f * x), -1.f); }
+
+// sigma(x) for the i, f, o gates and tanh(x) = 2 sigma(2x) - 1 for the g gate through one branch-free formula
+__device__ __forceinline__ float gate_act(float x, int g) {
+    const float s = g == 2 ? 2.f : 1.f;
+    const float sg = 1.f / (1.f + expf(-s * x));
+    return g == 2 ? fmaf(2.f, sg, -1.f) : sg;
+}
+
+template <int NW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+lstm_rec_fwd_c2_kernel(const float* __restrict__ w_hh, const float* gx, long long gx_tstride, float* act,
+                       float* __restrict__ hs, float* __restrict__ cs, float* __restrict__ hd, const uint8_t* __restrict__ mask,
+                       float scale, int T, int B) {
+    constexpr int H = 128, G4 = 512;
+    __shared__ __align__(16) float hbuf[2][NW][H];
+    __shared__ __align__(8) uint64_t full[2];                   // "the peer's half of h in buffer b has landed"
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int crank = cluster.block_rank();
+    const uint32_t hbuf_peer = mapa_u32(tc::smem_u32(&hbuf[0][0][0]), crank ^ 1u);
+    const uint32_t full_peer = mapa_u32(tc::smem_u32(&full[0]), crank ^ 1u);
+    const int j = threadIdx.x, g = j & 3, u = (int)crank * 64 + (j >> 2);
+    if (j == 0) { tc::mbar_init(&full[0], 1); tc::mbar_init(&full[1], 1); tc::fence_mbar_init(); }
+    const int r = g * H + u;                                    // the row whose activation this thread ends up with (gate g = k-slice id)
+    // A broadcast LDS.128 still costs 4 wavefronts (one per quarter warp), so h_{t-1} is NOT broadcast to one-row threads: the 4
+    // lanes of a unit split K -- lane g holds columns {16m + 4g .. 16m + 4g + 3, m < 8} of all FOUR gate rows of its unit (128
+    // registers; interleaved so the 4 lanes read 64 contiguous bytes: no bank conflict), reads only
+    // its 32 values of h (8 LDS.128 per window instead of 32, 4 distinct addresses per quarter warp) and a 3-shuffle
+    // reduce-scatter leaves the full sum of gate g in lane g (measured before: 0.7 us per window-step, LSU bound).
+    float wr[4][32];
+#pragma unroll
+    for (int gg = 0; gg < 4; ++gg)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) wr[gg][i] = w_hh[(size_t)(gg * H + u) * H + 16 * (i >> 2) + 4 * g + (i & 3)];
+    for (int i = j; i < 2 * NW * H; i += 256) (&hbuf[0][0][0])[i] = 0.f;
+    const int b0 = (blockIdx.x >> 1) * NW;
+    const int lane_base = (j & 31) & ~3;
+    float c[NW], pre[NW];
+    unsigned int mk[NW];
+    bool valid[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        c[w] = 0.f;
+        valid[w] = (b0 + w) < B;
+        pre[w] = valid[w] ? gx[(size_t)(b0 + w) * G4 + r] : 0.f;
+        mk[w] = (mask && valid[w] && g == 1) ? mask[((size_t)(b0 + w) * T) * H + u] : 1u;
+        if (valid[w] && g == 0) { hs[(size_t)(b0 + w) * H + u] = 0.f; cs[(size_t)(b0 + w) * H + u] = 0.f; }
+    }
+    cluster.sync();                              // buffers zeroed and barriers initialised before a peer writes into them
+    for (int t = 0; t < T; ++t) {
+        float a[NW];
+        unsigned int mcur[NW];
+        const int nbuf = (t + 1) & 1;
+        if (j == 0) tc::mbar_arrive_expect_tx(&full[nbuf], NW * 64 * 4);      // the peer's 64 units x NW windows of h_{t+1}
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { a[w] = pre[w]; mcur[w] = mk[w]; }
+        if (t + 1 < T) {                        // next step's inputs: issued a full step before they are consumed
+#pragma unroll
+            for (int w = 0; w < NW; ++w)
+                if (valid[w]) {
+                    pre[w] = gx[(size_t)(t + 1) * gx_tstride + (size_t)(b0 + w) * G4 + r];
+                    if (mask && g == 1) mk[w] = mask[((size_t)(b0 + w) * T + t + 1) * H + u];
+                }
+        }
+        const float* hb = &hbuf[t & 1][0][0] + 4 * g;
+        const int nb = nbuf * NW * H;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;         // this lane's K-slice of the four gate rows
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 h4 = *reinterpret_cast<const float4*>(hb + w * H + 4 * i);
+                p0 = fmaf(wr[0][i], h4.x, p0); p1 = fmaf(wr[1][i], h4.x, p1); p2 = fmaf(wr[2][i], h4.x, p2); p3 = fmaf(wr[3][i], h4.x, p3);
+                p0 = fmaf(wr[0][i + 1], h4.y, p0); p1 = fmaf(wr[1][i + 1], h4.y, p1); p2 = fmaf(wr[2][i + 1], h4.y, p2); p3 = fmaf(wr[3][i + 1], h4.y, p3);
+                p0 = fmaf(wr[0][i + 2], h4.z, p0); p1 = fmaf(wr[1][i + 2], h4.z, p1); p2 = fmaf(wr[2][i + 2], h4.z, p2); p3 = fmaf(wr[3][i + 2], h4.z, p3);
+                p0 = fmaf(wr[0][i + 3], h4.w, p0); p1 = fmaf(wr[1][i + 3], h4.w, p1); p2 = fmaf(wr[2][i + 3], h4.w, p2); p3 = fmaf(wr[3][i + 3], h4.w, p3);
+            }
+            // reduce-scatter over the 4 lanes of the unit: lane g ends with the full sum of gate g
+            const bool hi2 = (g & 2) != 0, hi1 = (g & 1) != 0;
+            const float r0 = __shfl_xor_sync(0xffffffffu, hi2 ? p0 : p2, 2);
+            const float r1 = __shfl_xor_sync(0xffffffffu, hi2 ? p1 : p3, 2);
+            const float k0 = (hi2 ? p2 : p0) + r0, k1 = (hi2 ? p3 : p1) + r1;
+            const float r2 = __shfl_xor_sync(0xffffffffu, hi1 ? k0 : k1, 1);
+            const float x = a[w] + ((hi1 ? k1 : k0) + r2);
+            const float sg = sigmoid_fast(g == 2 ? 2.f * x : x);
+            const float v = g == 2 ? fmaf(2.f, sg, -1.f) : sg;
+            const float gi = __shfl_sync(0xffffffffu, v, lane_base);
+            const float gf = __shfl_sync(0xffffffffu, v, lane_base + 1);
+            const float gg = __shfl_sync(0xffffffffu, v, lane_base + 2);
+            const float go = __shfl_sync(0xffffffffu, v, lane_base + 3);
+            c[w] = fmaf(gf, c[w], gi * gg);
+            const float h = go * tanh_fast(c[w]);
+            if (g == 0) (&hbuf[0][0][0])[nb + w * H + u] = h;
+            else if (g == 3) st_async_f32(hbuf_peer + (uint32_t)(nb + w * H + u) * 4u, h, full_peer + (uint32_t)nbuf * 8u);
+            if (valid[w]) {
+                const size_t tb = (size_t)t * B + (b0 + w);
+                act[tb * G4 + r] = v;
+                const size_t o = ((size_t)(t + 1) * B + (b0 + w)) * H + u;
+                if (g == 0) hs[o] = h;
+                else if (g == 2) cs[o] = c[w];
+                else if (g == 1 && hd) hd[tb * H + u] = mask ? (mcur[w] ? h * scale : 0.f) : h;
+            }
+        }
+        __syncthreads();                         // this CTA's half of h_{t+1} is in place, everyone is done reading h_t
+        // the peer's half: buffer 1 is used at t+1 = 1, 3, 5 ..., buffer 0 at t+1 = 2, 4, ...
+        tc::mbar_wait(&full[nbuf], (uint32_t)((((t + 1) >> 1) - (nbuf ? 0 : 1)) & 1));
+    }
+    cluster.sync();                              // no CTA leaves while its peer may still write into its shared memory
+}
+
+// Backward on the same cluster.  Phase A (thread <-> (unit 64c + (tid>>2), gate tid&3)): the pre-activation gradient of the thread's
+// gate row, written into BOTH CTAs' dG buffers; cluster barrier; phase B (thread <-> (k = 64c + (tid&63), quarter q = tid>>6)): the
+// partial dh_{t-1}[k] over the 128 rows of gate q with W_hh[.,k] in registers; block barrier; the next phase A sums the 4 partials.
+template <int NW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+lstm_rec_bwd_c2_kernel(const float* __restrict__ w_hh, float* act_dg, const float* __restrict__ cs,
+                       const float* __restrict__ dH, const uint8_t* __restrict__ mask, float scale,
+                       const float* __restrict__ dh_last, float* __restrict__ dgsum, int T, int B) {
+    constexpr int H = 128, G4 = 512, HL = 64;
+    __shared__ __align__(16) float dgs[2][NW][G4];                // double buffered: a fast CTA may already write step t-1
+    __shared__ float dhs[NW][HL];                                 // dh_{t-1}[k] of this CTA's 64 units (phase B -> next phase A)
+    __shared__ __align__(8) uint64_t full[2];
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int crank = cluster.block_rank();
+    const uint32_t dgs_peer = mapa_u32(tc::smem_u32(&dgs[0][0][0]), crank ^ 1u);
+    const uint32_t full_peer = mapa_u32(tc::smem_u32(&full[0]), crank ^ 1u);
+    const int tid = threadIdx.x;
+    if (tid == 0) { tc::mbar_init(&full[0], 1); tc::mbar_init(&full[1], 1); tc::fence_mbar_init(); }
+    const int g = tid & 3, ul = tid >> 2, u = (int)crank * HL + ul;      // phase A role
+    const int r = g * H + u;
+    // phase B role: thread <-> (4 columns k0..k0+3, rows n = 64m + 4*ns + j, m < 8, j < 4): 128 registers of W_hh^T; the 16 lanes
+    // of a column group read 256 contiguous bytes of dG (8 LDS.128 per window instead of 32 broadcast ones) and a 5-shuffle
+    // reduction leaves dh[k0 + (ns >> 2)] in every lane of the group
+    const int kg = tid >> 4, ns = tid & 15, k0 = (int)crank * HL + kg * 4;
+    float wreg[32][4];
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) wreg[i][jj] = w_hh[(size_t)(64 * (i >> 2) + 4 * ns + (i & 3)) * H + k0 + jj];
+    for (int i = tid; i < NW * HL; i += 256) (&dhs[0][0])[i] = 0.f;
+    const int b0 = (blockIdx.x >> 1) * NW;
+    const int lane_base = (tid & 31) & ~3;
+    float dc[NW], gs[NW], a_n[NW], ct_n[NW], cp_n[NW], dh_n[NW], dl_n[NW];
+    unsigned int mk_n[NW];
+    bool valid[NW];
+    auto fetch = [&](int t) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            if (!valid[w]) { a_n[w] = 0.f; ct_n[w] = 0.f; cp_n[w] = 0.f; dh_n[w] = 0.f; dl_n[w] = 0.f; mk_n[w] = 1u; continue; }
+            const int b = b0 + w;
+            const size_t tb = (size_t)t * B + b;
+            a_n[w] = act_dg[tb * G4 + r];
+            ct_n[w] = cs[((size_t)(t + 1) * B + b) * H + u];
+            cp_n[w] = cs[tb * H + u];
+            dh_n[w] = dH ? dH[tb * H + u] : 0.f;
+            mk_n[w] = mask ? mask[((size_t)b * T + t) * H + u] : 1u;
+            dl_n[w] = (dh_last && t == T - 1) ? dh_last[(size_t)b * H + u] : 0.f;
+        }
+    };
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { dc[w] = 0.f; gs[w] = 0.f; valid[w] = (b0 + w) < B; }
+    fetch(T - 1);
+    cluster.sync();
+    for (int t = T - 1; t >= 0; --t) {
+        float vc[NW], ct[NW], cp[NW], dho[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            vc[w] = a_n[w]; ct[w] = ct_n[w]; cp[w] = cp_n[w];
+            dho[w] = (mask ? (mk_n[w] ? dh_n[w] * scale : 0.f) : dh_n[w]) + dl_n[w];
+        }
+        if (t > 0) fetch(t - 1);
+        const int dbuf = t & 1;
+        const int db = dbuf * NW * G4;
+        if (tid == 0) tc::mbar_arrive_expect_tx(&full[dbuf], NW * 256 * 4);      // the peer's 256 rows x NW windows of dG_t
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const float dh = dho[w] + dhs[w][ul];
+            const float gi = __shfl_sync(0xffffffffu, vc[w], lane_base);
+            const float gf = __shfl_sync(0xffffffffu, vc[w], lane_base + 1);
+            const float gg = __shfl_sync(0xffffffffu, vc[w], lane_base + 2);
+            const float go = __shfl_sync(0xffffffffu, vc[w], lane_base + 3);
+            const float tch = tanh_fast(ct[w]);
+            const float dct = fmaf(dh * go, 1.f - tch * tch, dc[w]);
+            dc[w] = dct * gf;
+            float gv;
+            if (g == 0) gv = dct * gg * gi * (1.f - gi);            // d pre-act of i
+            else if (g == 1) gv = dct * cp[w] * gf * (1.f - gf);    // f
+            else if (g == 2) gv = dct * gi * (1.f - gg * gg);       // g
+            else gv = dh * tch * go * (1.f - go);                   // o
+            if (!valid[w]) gv = 0.f;
+            (&dgs[0][0][0])[db + w * G4 + r] = gv;
+            st_async_f32(dgs_peer + (uint32_t)(db + w * G4 + r) * 4u, gv, full_peer + (uint32_t)dbuf * 8u);
+            gs[w] += gv;
+            if (valid[w]) act_dg[((size_t)t * B + b0 + w) * G4 + r] = gv;
+        }
+        __syncthreads();                         // this CTA's rows of dG_t are in place
+        // the peer's rows: steps t = T-1, T-2, ... alternate the buffers; use n of buffer b is (T-1-t) >> 1
+        tc::mbar_wait(&full[dbuf], (uint32_t)(((T - 1 - t) >> 1) & 1));
+        const float* dg = &dgs[0][0][0] + db + 4 * ns;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;         // partial dh of the 4 columns over this lane's 32 rows
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const float4 d4 = *reinterpret_cast<const float4*>(dg + w * G4 + 64 * m);
+                p0 = fmaf(wreg[4 * m][0], d4.x, p0); p1 = fmaf(wreg[4 * m][1], d4.x, p1); p2 = fmaf(wreg[4 * m][2], d4.x, p2); p3 = fmaf(wreg[4 * m][3], d4.x, p3);
+                p0 = fmaf(wreg[4 * m + 1][0], d4.y, p0); p1 = fmaf(wreg[4 * m + 1][1], d4.y, p1); p2 = fmaf(wreg[4 * m + 1][2], d4.y, p2); p3 = fmaf(wreg[4 * m + 1][3], d4.y, p3);
+                p0 = fmaf(wreg[4 * m + 2][0], d4.z, p0); p1 = fmaf(wreg[4 * m + 2][1], d4.z, p1); p2 = fmaf(wreg[4 * m + 2][2], d4.z, p2); p3 = fmaf(wreg[4 * m + 2][3], d4.z, p3);
+                p0 = fmaf(wreg[4 * m + 3][0], d4.w, p0); p1 = fmaf(wreg[4 * m + 3][1], d4.w, p1); p2 = fmaf(wreg[4 * m + 3][2], d4.w, p2); p3 = fmaf(wreg[4 * m + 3][3], d4.w, p3);
+            }
+            // reduce-scatter over lane bits 3, 2 (column (ns >> 2) stays), then all-reduce over bits 1, 0
+            const bool hi8 = (ns & 8) != 0, hi4 = (ns & 4) != 0;
+            const float r0 = __shfl_xor_sync(0xffffffffu, hi8 ? p0 : p2, 8);
+            const float r1 = __shfl_xor_sync(0xffffffffu, hi8 ? p1 : p3, 8);
+            const float k0s = (hi8 ? p2 : p0) + r0, k1s = (hi8 ? p3 : p1) + r1;
+            const float r2 = __shfl_xor_sync(0xffffffffu, hi4 ? k0s : k1s, 4);
+            float v = (hi4 ? k1s : k0s) + r2;
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            if ((ns & 3) == 0) dhs[w][kg * 4 + (ns >> 2)] = v;
+        }
+        __syncthreads();
+    }
+    if (dgsum) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+            if (valid[w]) dgsum[(size_t)(b0 + w) * G4 + r] = gs[w];
+    }
+    cluster.sync();                              // no CTA leaves while its peer may still write into its shared memory
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -689,6 +951,18 @@ template <int H>
 static int launch_rec_fwd(cudaStream_t st, int nsm, const float* w_hh, const float* gx, long long tstride, float* act, float* hs,
                           float* cs, float* hd, const uint8_t* mask, float scale, int T, int B) {
     constexpr int KS = RecCfg<H>::KS;
+    if constexpr (H == 128) {
+        if (g_rec_cluster) {                       // two CTAs per cluster, W_hh in registers (see lstm_rec_fwd_c2_kernel)
+            const int pairs = nsm / 2;
+            const int nwc = B <= pairs ? 1 : (B <= 2 * pairs ? 2 : 4);
+            const int gridc = 2 * ((B + nwc - 1) / nwc);
+            if (nwc == 1) lstm_rec_fwd_c2_kernel<1><<<gridc, 256, 0, st>>>(w_hh, gx, tstride, act, hs, cs, hd, mask, scale, T, B);
+            else if (nwc == 2) lstm_rec_fwd_c2_kernel<2><<<gridc, 256, 0, st>>>(w_hh, gx, tstride, act, hs, cs, hd, mask, scale, T, B);
+            else lstm_rec_fwd_c2_kernel<4><<<gridc, 256, 0, st>>>(w_hh, gx, tstride, act, hs, cs, hd, mask, scale, T, B);
+            SHM_LAUNCH_CHECK();
+            return SHM_OK;
+        }
+    }
     const int nw = B <= nsm ? 1 : (B <= 2 * nsm ? 2 : 4);
     const size_t smem = (size_t)(KS / 4) * 4 * H * sizeof(float4) + (size_t)2 * nw * H * sizeof(float);
     const int grid = (B + nw - 1) / nw;
@@ -708,6 +982,18 @@ template <int H>
 static int launch_rec_bwd(cudaStream_t st, int nsm, const float* w_hh, float* act_dg, const float* cs, const float* dH,
                           const uint8_t* mask, float scale, const float* dh_last, float* dgsum, int T, int B) {
     constexpr int MS = RecCfg<H>::MS;
+    if constexpr (H == 128) {
+        if (g_rec_cluster) {
+            const int pairs = nsm / 2;
+            const int nwc = B <= pairs ? 1 : (B <= 2 * pairs ? 2 : 4);
+            const int gridc = 2 * ((B + nwc - 1) / nwc);
+            if (nwc == 1) lstm_rec_bwd_c2_kernel<1><<<gridc, 256, 0, st>>>(w_hh, act_dg, cs, dH, mask, scale, dh_last, dgsum, T, B);
+            else if (nwc == 2) lstm_rec_bwd_c2_kernel<2><<<gridc, 256, 0, st>>>(w_hh, act_dg, cs, dH, mask, scale, dh_last, dgsum, T, B);
+            else lstm_rec_bwd_c2_kernel<4><<<gridc, 256, 0, st>>>(w_hh, act_dg, cs, dH, mask, scale, dh_last, dgsum, T, B);
+            SHM_LAUNCH_CHECK();
+            return SHM_OK;
+        }
+    }
     const int nw = B <= nsm ? 1 : (B <= 2 * nsm ? 2 : 4);
     const size_t smem = (size_t)(MS / 4) * 2 * H * sizeof(float4) + (size_t)(nw * 4 * H + 2 * nw * H) * sizeof(float);
     const int grid = (B + nw - 1) / nw;
@@ -1027,6 +1313,9 @@ extern "C" int shm_adamw_clip_step(float* params, const float* grads, float* exp
 }
 
 extern "C" int shm_train_set_tensor_cores(int enable) {
-    shm::g_train_tc = enable ? 1 : 0;
+    // 0: fp32 FMA contractions + single-CTA recurrence (the r01 engines); 1: both r02 engines (default);
+    // 2: cluster recurrence only; 3: same as 1; 5: tensor-core contractions only
+    shm::g_train_tc = (enable == 1 || enable == 3 || enable == 5) ? 1 : 0;
+    shm::g_rec_cluster = (enable == 1 || enable == 2 || enable == 3) ? 1 : 0;
     return SHM_OK;
 }

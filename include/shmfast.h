@@ -219,7 +219,8 @@ int shm_adam_clip_step(float* params, const float* grads, float* exp_avg, float*
  *   split on the fly into 16-bit hi/lo halves, 3 MMA passes, fp32 accumulation in TMEM (fp16 halves: 2^-22 relative with an
  *   absolute floor of 2^-25, for O(1) activations; bf16 halves: 2^-16 relative over fp32's whole range, for gradients); shapes
  *   that do not qualify (small, or not float4-loadable along a contiguous dimension) run on the FMA pipe.
- * shm_train_set_tensor_cores(0) keeps every contraction of the training steps on the FMA pipe (default 1). */
+ * shm_train_set_tensor_cores: 1 (default) = tensor-core contractions + the two-CTA-cluster recurrence for H = 128; 0 = the fp32 FMA
+ * contractions and single-CTA recurrence kernels; 2 = cluster recurrence only; 5 = tensor-core contractions only. */
 enum { SHM_GEMM_SIMT = 0, SHM_GEMM_TC_F16X3 = 1, SHM_GEMM_TC_BF16X3 = 2 };
 int shm_gemm_f32(const float* A, int64_t a_ms, int64_t a_ks, const float* B, int64_t b_ks, int64_t b_ns, float* C, int64_t ldc,
                  int32_t M, int32_t N, int32_t K, const float* bias, int32_t splitk, int32_t mode, void* stream);
