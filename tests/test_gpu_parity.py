@@ -311,6 +311,11 @@ def test_onedof_stitch_rmse(cuda_dev, golden_dir):
     assert src.n_windows == int(g["n_windows"])
     W = ops.window_normalize(src)
     assert np.array_equal(W[:4].cpu().numpy(), g["windows_f32_head"])
+    # ALL windows: the reference's standardised series (datasets.standardize, cast to fp32 like 04_test_seen_variants.py:292) --
+    # every window the reference builds is a slice of it
+    ref_all = np.lib.stride_tricks.sliding_window_view(g["norm_series_f32"], 80, axis=0).transpose(0, 2, 1)
+    assert ref_all.shape == tuple(W.shape) and np.array_equal(W.cpu().numpy(), ref_all)
+    assert np.array_equal(W.cpu().numpy().astype(np.float64).sum(axis=(1, 2)), g["windows_checksum"])
     m = onedof.TemporalVAE().to(cuda_dev).eval()
     m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
     eps = synth.eps(src.n_windows, 5, seed=int(g["seed"]))
@@ -431,3 +436,84 @@ def test_full_size_properties_openlab(cuda_dev, N):
     Wk = Wm[:k].cpu().numpy()
     ro, _, _ = O.vae_forward(sd, Wk, e_sel[:k].cpu().numpy(), np.float64)
     assert rel_err(a[sel[:k].long()].cpu().numpy(), O.mse_score(Wk.astype(np.float64), ro)) < REL_TOL
+
+
+def test_4dof_hybrid_at_the_repos_flag_rate_vs_port(cuda_dev):
+    """BASELINE configs[2] at the repo's real test-set flag rate (47 %): 8,192 windows gathered from a
+    series, scored, thresholded at the score's P53, second pass + CNN on ~3,850 flagged windows -- every score / flag / index / logit /
+    label against the reference's wiring on torch CPU kernels (oracle.torch_port.hybrid_4dof, same eps).  Band windows are counted."""
+    from oracle import torch_port as TP
+    N, T, D, Z = 8192, 100, 12, 16
+    vae_sd, cnn_sd = synth.stage_vae_weights("4dof", seed=11, scale=2.0), synth.cnn4dof_weights(seed=11)
+    series = synth.series(N + T - 1, D, seed=11)
+    mean, std = synth.stats(D, seed=11)
+    std = guard_std_4dof(std)
+    eps1, eps2 = synth.eps(N, Z, seed=12), synth.eps(N, Z, seed=13)
+    port_v, port_c = TP.VaePort(vae_sd), TP.Cnn4dofPort(cnn_sd)
+    W = np.stack([series[i:i + T] for i in range(N)]).astype(np.float32)
+    Zw = np.nan_to_num((W - mean[None, None]) / std[None, None], nan=0.0, posinf=0.0, neginf=0.0).astype(np.float32)
+    s_ref = TP.vae_scores_batched(port_v, Zw, eps1, 512)
+    ss = np.sort(s_ref.astype(np.float64))
+    k53 = int(0.53 * N)
+    thr = float(0.5 * (ss[k53 - 1] + ss[k53]))                       # P53, placed mid-gap
+    ref = TP.hybrid_4dof(port_v, port_c, series, mean, std, thr, eps1=eps1, eps2=eps2)
+    n_ref = int(ref["idx"].size)
+    assert 0.45 * N < n_ref < 0.49 * N
+    vae, cnn = ops.VaeScorer(vae_sd, cuda_dev), ops.Cnn4dof(cnn_sd, cuda_dev)
+    src = ops.WindowSource(to_dev(series, cuda_dev), T, stride=1, mean=mean, std=std, nan_to_zero=True)
+    res = Hybrid4dof(vae, cnn, thr).run_dense(src, to_dev(eps1, cuda_dev), to_dev(eps2, cuda_dev))
+    torch.cuda.synchronize()
+    score = res["score"].cpu().numpy()
+    assert rel_err(score, ref["score"]) < REL_TOL
+    band = flags_match_outside_band(score, ref["score"], thr, res["flag"].cpu().numpy())
+    st = res["status"].cpu().numpy()
+    assert st[1] == 0
+    if band == 0:
+        assert st[0] == n_ref and np.array_equal(res["idx"][:n_ref].cpu().numpy(), ref["idx"])
+        lg = res["logits"][:n_ref].cpu().numpy()
+        assert np.allclose(lg, ref["logits"], rtol=REL_TOL, atol=LOGIT_ABS)
+        tie = np.abs(ref["logits"][:, 0] - ref["logits"][:, 1]) <= 2 * LOGIT_ABS          # argmax may flip only on a logit tie
+        y = res["y_pred"].cpu().numpy()
+        assert np.array_equal(y[ref["idx"]][~tie], ref["y_pred"][ref["idx"]][~tie])
+        assert int((y != 0).sum()) == n_ref
+        assert np.allclose(res["p_full"].cpu().numpy(), ref["p_struct"], atol=2e-4)
+    print(f"4DOF 47 %: flagged {n_ref}/{N}, band {band}, score rel err {rel_err(score, ref['score']):.2e}")
+
+
+def test_openlab_hybrid_at_the_repos_flag_rate_vs_port(cuda_dev):
+    """BASELINE configs[3] at the repo's real test-set flag rate (38 %): 4,096 windows (T 200, stride 20, NaN runs
+    in the raw channels), gate on 3 channels, CNN on the flagged raw windows with its own statistics; vs oracle.torch_port.hybrid_openlab."""
+    from oracle import torch_port as TP
+    N = 4096
+    vae_sd, cnn_sd = synth.stage_vae_weights("openlab", seed=21, scale=2.0), synth.cnnol_weights(seed=21)
+    series = synth.series((N - 1) * 20 + 200, 4, seed=21, nan_frac=0.0007)
+    vmu, vsd = synth.stats(3, seed=1)
+    cmu, csd = synth.stats(4, seed=2)
+    eps = synth.eps(N, 8, seed=22)
+    port_v, port_c = TP.VaePort(vae_sd), TP.CnnOpenLabPort(cnn_sd)
+    first = TP.hybrid_openlab(port_v, port_c, series, [1, 2, 3], vmu, vsd, cmu, csd, float("inf"), 0.5, eps=eps)
+    ss = np.sort(first["score"].astype(np.float64))
+    k62 = int(0.62 * N)
+    thr = float(0.5 * (ss[k62 - 1] + ss[k62]))
+    ref = TP.hybrid_openlab(port_v, port_c, series, [1, 2, 3], vmu, vsd, cmu, csd, thr, 0.13, eps=eps)
+    n_ref = int(ref["mask"].sum())
+    assert 0.36 * N < n_ref < 0.40 * N
+    vae, cnn = ops.VaeScorer(vae_sd, cuda_dev), ops.CnnOpenLab(cnn_sd, cuda_dev)
+    sd = to_dev(series, cuda_dev)
+    g = ops.WindowSource(sd, 200, stride=20, chan=[1, 2, 3], mean=vmu, std=vsd, clip=10.0, nan_to_zero=True)
+    r = ops.WindowSource(sd, 200, stride=20, mean=cmu, std=csd, clip=10.0, nan_to_zero=True)
+    res = HybridOpenLab(vae, cnn, thr, 0.13).run_dense(g, r, to_dev(eps, cuda_dev))
+    torch.cuda.synchronize()
+    score = res["score"].cpu().numpy()
+    assert rel_err(score, ref["score"]) < REL_TOL
+    band = flags_match_outside_band(score, ref["score"], thr, res["flag"].cpu().numpy())
+    if band == 0:
+        assert int(res["status"][0].item()) == n_ref
+        assert np.array_equal(res["idx"][:n_ref].cpu().numpy(), np.where(ref["mask"])[0])
+        prob = res["prob"][:n_ref].cpu().numpy()
+        assert prob.dtype == np.float64 and np.allclose(prob, ref["prob"], rtol=REL_TOL, atol=2e-4)
+        near = np.abs(ref["prob"] - 0.13) < 2e-4
+        assert np.array_equal(res["pred"][:n_ref].cpu().numpy()[~near], ref["pred"][~near])
+        y3 = res["y_pred"].cpu().numpy()
+        assert int((y3 != 0).sum()) == n_ref and np.array_equal(y3[np.where(ref["mask"])[0]][~near], 1 + ref["pred"][~near])
+    print(f"openLAB 38 %: flagged {n_ref}/{N}, band {band}, score rel err {rel_err(score, ref['score']):.2e}")

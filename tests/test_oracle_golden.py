@@ -76,6 +76,8 @@ def test_onedof_stitch_rmse(golden_dir):
     assert W.shape[0] == int(g["n_windows"])
     xb = W.astype(np.float32)
     assert np.array_equal(xb[:4], g["windows_f32_head"])
+    ref_all = np.lib.stride_tricks.sliding_window_view(g["norm_series_f32"], 80, axis=0).transpose(0, 2, 1)     # all 1,422 windows
+    assert np.array_equal(xb, ref_all)
     eps = synth.eps(W.shape[0], 5, seed=int(g["seed"]))
     recon, mu, _ = O.vae_forward(sd, xb, eps, np.float32)
     assert np.allclose(mu, g["mu"], rtol=2e-5, atol=2e-6)
