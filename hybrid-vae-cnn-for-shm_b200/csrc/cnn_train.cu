@@ -202,23 +202,37 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const ConvG s, const fl
     }
 }
 
-// out[c] = sum_{b,hw} src[b,c,hw]   (convolution bias gradient); one CTA per channel, fixed summation order
-__global__ void __launch_bounds__(256) chan_sum_kernel(const float* __restrict__ src, int B, int C, int HW, float* __restrict__ out) {
-    const int c = blockIdx.x;
-    double s = 0.0;
-    const int n = B * HW;
+// part[(c*S + s)*2 + {0,1}] = sum / sum of squares of src[b,c,hw] over the samples of split s (blockIdx.y), fp64, fixed order;
+// used for the convolution bias gradient (sum only) and the BatchNorm batch statistics.  r02: 16-32 CTAs walking 120 k
+// elements each took 150-170 us per call (profiles/r02_launches_cnn_train_4dof.csv): the batch is now split over gridDim.y CTAs.
+__global__ void __launch_bounds__(256) chan_partial_kernel(const float* __restrict__ src, int B, int C, int HW, int b_per_split,
+                                                           double* __restrict__ part) {
+    const int c = blockIdx.x, S = gridDim.y, sp = blockIdx.y;
+    const int b_beg = sp * b_per_split, b_end = min(B, b_beg + b_per_split);
+    double s = 0.0, q = 0.0;
+    const int n = max(0, b_end - b_beg) * HW;
     for (int i = threadIdx.x; i < n; i += 256) {
-        const int b = i / HW, hw = i - b * HW;
-        s += (double)src[((size_t)b * C + c) * HW + hw];
+        const int b = b_beg + i / HW, hw = i % HW;
+        const double v = src[((size_t)b * C + c) * HW + hw];
+        s += v; q += v * v;
     }
-    __shared__ double red[256];
-    red[threadIdx.x] = s;
+    __shared__ double rs_[256], rq_[256];
+    rs_[threadIdx.x] = s; rq_[threadIdx.x] = q;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        if (threadIdx.x < o) { rs_[threadIdx.x] += rs_[threadIdx.x + o]; rq_[threadIdx.x] += rq_[threadIdx.x + o]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[c] = (float)red[0];
+    if (threadIdx.x == 0) { part[((size_t)c * S + sp) * 2] = rs_[0]; part[((size_t)c * S + sp) * 2 + 1] = rq_[0]; }
+}
+
+// out[c] = sum over the S partials (fixed order)
+__global__ void chan_sum_final_kernel(const double* __restrict__ part, int C, int S, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int i = 0; i < S; ++i) s += part[((size_t)c * S + i) * 2];
+    out[c] = (float)s;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -284,6 +298,26 @@ __global__ void __launch_bounds__(256) norm_stats_kernel(const NormBlk k, const 
             running_mean[blockIdx.x] = (float)((1.0 - momentum) * running_mean[blockIdx.x] + momentum * mean);
             running_var[blockIdx.x] = (float)((1.0 - momentum) * running_var[blockIdx.x] + momentum * unb);
         }
+    }
+}
+
+// BatchNorm statistics from the (C, S) partials of chan_partial_kernel: mean / rstd per channel + running-stat update
+__global__ void bn_stats_final_kernel(const NormBlk k, const double* __restrict__ part, int S, float* __restrict__ running_mean,
+                                      float* __restrict__ running_var, float momentum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= k.C) return;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < S; ++i) { s += part[((size_t)c * S + i) * 2]; q += part[((size_t)c * S + i) * 2 + 1]; }
+    const double count = (double)k.B * k.H * k.W;
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    k.mu[c] = (float)mean;
+    k.rs[c] = (float)(1.0 / sqrt(var + (double)k.eps));
+    if (running_mean && running_var) {           // nn.BatchNorm2d: running = (1-m)*running + m*stat, unbiased variance
+        const double unb = count > 1 ? var * count / (count - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
     }
 }
 
@@ -542,7 +576,7 @@ struct shm_cnn_trainer {
     size_t ws_floats;
     // workspace offsets (floats)
     size_t y[4], act[4], mu[4], rs[4], wf[4], wb[4];
-    size_t u, vd, dlg_u, dvd, dfeat, dy, da, pb, pg, m1, m2;
+    size_t u, vd, dlg_u, dvd, dfeat, dy, da, pb, pg, m1, m2, part;
     uint8_t* mask;
     int B, have_fwd, use_mask;
     float drop_scale;
@@ -589,6 +623,7 @@ extern "C" int shm_cnn_trainer_create(shm_cnn_trainer** out, int arch, int32_t m
     h->dy = take(max_y); h->da = take(max_a);
     h->pb = take(B * max_c); h->pg = take(B * max_c);
     h->m1 = take(B * 8 > max_c ? B * 8 : max_c); h->m2 = take(B * 8 > max_c ? B * 8 : max_c);
+    h->part = take((size_t)256 * 32 * 2 * 2);          // fp64 [C <= 256][S <= 32][2] partial sums
     h->ws_floats = o;
     if (cudaMalloc(&h->ws, o * sizeof(float)) != cudaSuccess || cudaMalloc(&h->mask, B * h->a.HID) != cudaSuccess) {
         set_cuda_error(cudaGetLastError(), "cudaMalloc(cnn trainer)");
@@ -632,6 +667,16 @@ static inline int ew_grid(long long n, int nsm) {
     return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
+// batch splits for the per-channel reductions: enough CTAs to fill the GPU, at most 32 per channel
+static inline void chan_splits(int B, int C, int nsm, int* S, int* bps) {
+    int s = (2 * nsm + C - 1) / C;
+    if (s > 32) s = 32;
+    if (s > B) s = B;
+    if (s < 1) s = 1;
+    *bps = (B + s - 1) / s;
+    *S = (B + *bps - 1) / *bps;
+}
+
 extern "C" int shm_cnn_train_forward(shm_cnn_trainer* h, const float* params, const float* x, int32_t B, float* bn_running,
                                      float bn_momentum, const uint8_t* drop_mask, float drop_p, float* logits, void* stream) {
     if (!h || !params || !x || !logits || B < 1 || B > h->Bmax || drop_p < 0.f || drop_p >= 1.f) return SHM_ERR_ARG;
@@ -654,7 +699,16 @@ extern "C" int shm_cnn_train_forward(shm_cnn_trainer* h, const float* params, co
         const NormBlk k = norm_blk(h, params, i, B);
         float* rm = nullptr; float* rv = nullptr;
         if (b.norm == 0 && bn_running) { rm = bn_running + run_off; rv = bn_running + run_off + b.Cout; run_off += 2 * (size_t)b.Cout; }
-        norm_stats_kernel<<<b.norm == 0 ? b.Cout : B * 8, 256, 0, st>>>(k, ws + h->y[i], rm, rv, bn_momentum);
+        if (b.norm == 0) {
+            int S, bps;
+            chan_splits(B, b.Cout, h->nsm, &S, &bps);
+            double* part = reinterpret_cast<double*>(ws + h->part);
+            chan_partial_kernel<<<dim3(b.Cout, S), 256, 0, st>>>(ws + h->y[i], B, b.Cout, b.H * b.W, bps, part);
+            SHM_LAUNCH_CHECK();
+            bn_stats_final_kernel<<<(b.Cout + 63) / 64, 64, 0, st>>>(k, part, S, rm, rv, bn_momentum);
+        } else {
+            norm_stats_kernel<<<B * 8, 256, 0, st>>>(k, ws + h->y[i], rm, rv, bn_momentum);
+        }
         SHM_LAUNCH_CHECK();
         const long long n_out = b.gap ? (long long)B * b.Cout * 32 : (long long)B * b.Cout * (b.H / b.ph) * (b.W / b.pw);
         norm_act_pool_fwd_kernel<<<b.gap ? (unsigned)((n_out + 255) / 256) : ew_grid(n_out, h->nsm), 256, 0, st>>>(k, ws + h->y[i], ws + h->act[i]);
@@ -714,8 +768,15 @@ extern "C" int shm_cnn_train_backward(shm_cnn_trainer* h, const float* params, c
         norm_bwd_apply_kernel<<<ew_grid((long long)B * b.Cout * b.H * b.W, h->nsm), 256, 0, st>>>(k, ws + h->y[i], ws + h->dy, ws + h->m1, ws + h->m2);
         SHM_LAUNCH_CHECK();
         // convolution: bias, weight, (data)
-        chan_sum_kernel<<<b.Cout, 256, 0, st>>>(ws + h->dy, B, b.Cout, b.H * b.W, grads + L.cb[i]);
-        SHM_LAUNCH_CHECK();
+        {
+            int S, bps;
+            chan_splits(B, b.Cout, h->nsm, &S, &bps);
+            double* part = reinterpret_cast<double*>(ws + h->part);
+            chan_partial_kernel<<<dim3(b.Cout, S), 256, 0, st>>>(ws + h->dy, B, b.Cout, b.H * b.W, bps, part);
+            SHM_LAUNCH_CHECK();
+            chan_sum_final_kernel<<<(b.Cout + 63) / 64, 64, 0, st>>>(part, b.Cout, S, grads + L.cb[i]);
+            SHM_LAUNCH_CHECK();
+        }
         const ConvG g = conv_g(b, B);
         const float* xin = i == 0 ? h->x_in : ws + h->act[i - 1];
         const int Nw = b.Cin * b.KH * b.KW;

@@ -31,8 +31,14 @@ struct TcGemmArgs {
     int kchunk, atomic, a_kcontig, b_kcontig, bf16;
 };
 
-// 128 rows x 32 k of an operand whose element (r, k) sits at P[r*rs + k*ks]; 4 float4 per thread.
-// kcontig (ks == 1): lanes run along k;  otherwise (rs == 1): lanes run along the rows.
+// 128 rows x 32 k of an operand whose element (r, k) sits at P[r*rs + k*ks]; 4 float4 per thread, each ending up as 4 consecutive
+// k of ONE row (what the 8-byte core-matrix store wants).
+//   kcontig (ks == 1): item W = e*8 + warp -> row group g = W>>1 (8 rows), k half W&1; lane -> row g*8 + (lane&7), k quad (W&1)*4 + (lane>>3):
+//     a warp reads 8 rows x 64 B and writes 2 x 128 contiguous bytes per image.
+//   otherwise (rs == 1): lanes run along the rows -- lane = (row quad mq = lane&3, kk = (lane>>2)&3, k-quad parity kh = lane>>4) reads
+//     rows rb*16 + 4mq..+3 at k = ko*8 + kh*4 + kk (W -> rb = W&7, ko = W>>3), then a 4x4 transpose over the 4 lanes that differ in kk
+//     (4 shuffles) leaves row rb*16 + 4mq + kk, k = ko*8 + kh*4..+3 in the lane: the warp then writes 256 contiguous bytes per image.
+//     (r02 first version: 2-byte scattered stores, 5.7 M bank conflicts per dW launch -- profiles/r02_tc_gemm_raw.csv.)
 __device__ __forceinline__ void gt_load(const float* __restrict__ P, long long rs, long long ks, int rows_valid, int k0, int kend,
                                         bool kcontig, float4 (&v)[4]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -45,12 +51,23 @@ __device__ __forceinline__ void gt_load(const float* __restrict__ P, long long r
             const int k = k0 + ((W & 1) * 4 + (lane >> 3)) * 4;
             if (row < rows_valid && k < kend) f = __ldg(reinterpret_cast<const float4*>(P + (long long)row * rs + k));
         } else {
-            const int row0 = (W & 3) * 32 + (lane & 7) * 4;
-            const int k = k0 + (W >> 2) * 4 + (lane >> 3);
+            const int row0 = (W & 7) * 16 + (lane & 3) * 4;
+            const int k = k0 + (W >> 3) * 8 + (lane >> 4) * 4 + ((lane >> 2) & 3);
             if (row0 < rows_valid && k < kend) f = __ldg(reinterpret_cast<const float4*>(P + (long long)k * ks + row0));
         }
         v[e] = f;
     }
+}
+
+// 4x4 transpose over the 4 lanes that differ in lane bits 2..3: in: lane kk holds X[row 0..3][k = kk]; out: X[row = kk][k 0..3]
+__device__ __forceinline__ float4 gt_transpose4(float4 a, int kk) {
+    const bool hiA = (kk & 2) != 0, hiB = (kk & 1) != 0;
+    const float r0 = __shfl_xor_sync(0xffffffffu, hiA ? a.x : a.z, 8);
+    const float r1 = __shfl_xor_sync(0xffffffffu, hiA ? a.y : a.w, 8);
+    const float t0 = hiA ? r0 : a.x, t1 = hiA ? r1 : a.y, t2 = hiA ? a.z : r0, t3 = hiA ? a.w : r1;
+    const float s0 = __shfl_xor_sync(0xffffffffu, hiB ? t0 : t1, 4);
+    const float s1 = __shfl_xor_sync(0xffffffffu, hiB ? t2 : t3, 4);
+    return make_float4(hiB ? s0 : t0, hiB ? t1 : s0, hiB ? s1 : t2, hiB ? t3 : s1);
 }
 
 // registers -> hi / lo K-major core-matrix images: byte offset(r, k) = (k/8)*2048 + (r/8)*128 + (r%8)*16 + (k%8)*2
@@ -59,28 +76,23 @@ __device__ __forceinline__ void gt_store(const float4 (&v)[4], unsigned char* hi
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int W = e * 8 + warp;
-        uint32_t h0, l0, h1, l1;
-        if (bf16) { split_bf16x2(v[e].x, v[e].y, h0, l0); split_bf16x2(v[e].z, v[e].w, h1, l1); }
-        else { split_f16x2(v[e].x, v[e].y, h0, l0); split_f16x2(v[e].z, v[e].w, h1, l1); }
+        float4 x = v[e];
+        int row, kq;                                  // this lane's row and k quad (4 consecutive k) of the 128 x 32 tile
         if (kcontig) {
-            const int g = W >> 1, r8 = lane & 7, kq = (W & 1) * 4 + (lane >> 3);
-            const uint32_t off = (uint32_t)(kq >> 1) * 2048u + (uint32_t)g * 128u + (uint32_t)r8 * 16u + (uint32_t)(kq & 1) * 8u;
-            *reinterpret_cast<uint2*>(hi_img + off) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(lo_img + off) = make_uint2(l0, l1);
+            row = (W >> 1) * 8 + (lane & 7);
+            kq = (W & 1) * 4 + (lane >> 3);
         } else {
-            const int row0 = (W & 3) * 32 + (lane & 7) * 4;
-            const int k = (W >> 2) * 4 + (lane >> 3);
-            const uint32_t kb = (uint32_t)(k >> 3) * 2048u + (uint32_t)(k & 7) * 2u;
-            const uint16_t hh[4] = {(uint16_t)(h0 & 0xffffu), (uint16_t)(h0 >> 16), (uint16_t)(h1 & 0xffffu), (uint16_t)(h1 >> 16)};
-            const uint16_t ll[4] = {(uint16_t)(l0 & 0xffffu), (uint16_t)(l0 >> 16), (uint16_t)(l1 & 0xffffu), (uint16_t)(l1 >> 16)};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int row = row0 + j;
-                const uint32_t off = kb + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
-                *reinterpret_cast<uint16_t*>(hi_img + off) = hh[j];
-                *reinterpret_cast<uint16_t*>(lo_img + off) = ll[j];
-            }
+            const int kk = (lane >> 2) & 3;
+            x = gt_transpose4(x, kk);
+            row = (W & 7) * 16 + (lane & 3) * 4 + kk;
+            kq = (W >> 3) * 2 + (lane >> 4);
         }
+        uint32_t h0, l0, h1, l1;
+        if (bf16) { split_bf16x2(x.x, x.y, h0, l0); split_bf16x2(x.z, x.w, h1, l1); }
+        else { split_f16x2(x.x, x.y, h0, l0); split_f16x2(x.z, x.w, h1, l1); }
+        const uint32_t off = (uint32_t)(kq >> 1) * 2048u + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u + (uint32_t)(kq & 1) * 8u;
+        *reinterpret_cast<uint2*>(hi_img + off) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(lo_img + off) = make_uint2(l0, l1);
     }
 }
 
