@@ -22,7 +22,8 @@ struct ConvG {            // stride-1 convolution with "same" padding, NCHW
     int B, Cin, Cout, H, W, KH, KW, PH, PW;
 };
 
-// W[co][ci][khw] -> Wf[(ci*KHW + khw)][co] (forward operand) and Wb[(co*KHW + khw)][ci] (backward-data operand)
+// W[co][ci][khw] -> Wf[(khw*Cin + ci)][co] (forward operand) and Wb[(khw*Cout + co)][ci] (backward-data operand): TAP-major K, so
+// that a 16-wide K tile of the implicit GEMM is 16 channels at ONE filter tap (no per-element index arithmetic in the loader)
 __global__ void conv_repack_kernel(const float* __restrict__ W, int Cout, int Cin, int KHW, float* __restrict__ Wf,
                                    float* __restrict__ Wb) {
     const int n = Cout * Cin * KHW;
@@ -31,15 +32,18 @@ __global__ void conv_repack_kernel(const float* __restrict__ W, int Cout, int Ci
         const int r = i - co * (Cin * KHW);
         const int ci = r / KHW, khw = r - ci * KHW;
         const float v = W[i];
-        Wf[(size_t)(ci * KHW + khw) * Cout + co] = v;
-        Wb[(size_t)(co * KHW + khw) * Cin + ci] = v;
+        Wf[(size_t)(khw * Cin + ci) * Cout + co] = v;
+        Wb[(size_t)(khw * Cout + co) * Cin + ci] = v;
     }
 }
 
-// MODE 0 (forward):       dst[b,n,h,w] = bias[n] + sum_{ci,kh,kw} src[b,ci,h+kh-PH,w+kw-PW] * Wm[(ci,kh,kw)][n],  n < Cout
-// MODE 1 (backward data): dst[b,n,h,w] =           sum_{co,kh,kw} src[b,co,h-kh+PH,w-kw+PW] * Wm[(co,kh,kw)][n],  n < Cin
-// GEMM view: M = B*H*W rows (b,h,w), K = Csrc*KH*KW, N columns; 64x64x16 tiles, 256 threads, 4x4 per thread with the
-// rows interleaved (m = i*16 + lane-in-16) so global loads and stores run along w.
+// MODE 0 (forward):       dst[b,n,h,w] = bias[n] + sum_{kh,kw,ci} src[b,ci,h+kh-PH,w+kw-PW] * Wm[(kh,kw,ci)][n],  n < Cout
+// MODE 1 (backward data): dst[b,n,h,w] =           sum_{kh,kw,co} src[b,co,h-kh+PH,w-kw+PW] * Wm[(kh,kw,co)][n],  n < Cin
+// GEMM view: M = B*H*W rows (b,h,w), K = KH*KW*Csrc (tap-major: ncu showed the channel-major loader spending 40 % of all issue slots
+// on ALU index arithmetic, FMA 38 % -- profiles/r02_cnn_train_conv_raw.csv), N columns; 128 x 64 x 16 tiles, 256 threads, 8 x 4 per thread (two groups of 4
+// consecutive rows: LDS.128 for both operands, 3 loads per 32 FMAs, float4 stores along w -- H*W is a multiple of 4 in every
+// block, so a row quad never straddles a sample).  r02 first version: 64 x 64 tiles, 4 x 4 per thread, 5 loads per 16 FMAs.
+constexpr int CI_BM = 128, CI_BN = 64;
 template <int MODE>
 __global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvG s, const float* __restrict__ src, const float* __restrict__ Wm,
                                                          const float* __restrict__ bias, float* __restrict__ dst) {
@@ -47,77 +51,99 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvG s, const fl
     const int Csrc = MODE == 0 ? s.Cin : s.Cout;
     const int N = MODE == 0 ? s.Cout : s.Cin;
     const int M = s.B * HW, K = Csrc * KHW;
-    __shared__ __align__(16) float As[CT_BK][CT_BM + 4];
-    __shared__ __align__(16) float Bs[CT_BK][CT_BN + 4];
+    __shared__ __align__(16) float As[CT_BK][CI_BM + 4];
+    __shared__ __align__(16) float Bs[CT_BK][CI_BN + 4];
     const int tid = threadIdx.x, tm = tid & 15, tn = tid >> 4;
-    const int m0 = blockIdx.x * CT_BM, n0 = blockIdx.y * CT_BN;
-    // loader coordinates: this thread always loads row m_l of A and column n_l of B, k = (tid >> 6) + 4e
-    const int m_l = tid & 63, kq = tid >> 6;
+    const int m0 = blockIdx.x * CI_BM, n0 = blockIdx.y * CI_BN;
+    // loader coordinates: A: row m_l, k = (tid >> 7) + 2e (8 per thread);  B: column n_l, k = (tid >> 6) + 4e (4 per thread)
+    const int m_l = tid & 127, kqa = tid >> 7;
     const int gm = m0 + m_l;
     const bool m_ok = gm < M;
     const int b_l = m_ok ? gm / HW : 0;
     const int hw_l = m_ok ? gm - b_l * HW : 0;
     const int h_l = hw_l / s.W, w_l = hw_l - h_l * s.W;
     const float* src_b = src + (size_t)b_l * Csrc * HW;
-    const int gn_l = n0 + m_l;
+    const int n_l = tid & 63, kqb = tid >> 6;
+    const int gn_l = n0 + n_l;
     const bool n_ok = gn_l < N;
-    float acc[4][4];
+    float acc[8][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    float ra[4], rb[4];
+    float ra[8], rb[4];
+    const bool fast = (Csrc % CT_BK) == 0;                 // a K tile never straddles a filter tap
     auto fetch = [&](int k0) {
+        if (fast) {
+            const int tap = k0 / Csrc, c0 = k0 - tap * Csrc;
+            const int kh = tap / s.KW, kw = tap - kh * s.KW;
+            const int hh = MODE == 0 ? h_l + kh - s.PH : h_l - kh + s.PH;
+            const int ww = MODE == 0 ? w_l + kw - s.PW : w_l - kw + s.PW;
+            const bool ok = m_ok && hh >= 0 && hh < s.H && ww >= 0 && ww < s.W;
+            const float* base = src_b + (size_t)(c0 + kqa) * HW + hh * s.W + ww;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int k = k0 + kq + 4 * e;
-            float a = 0.f, bv = 0.f;
-            if (k < K) {
-                if (m_ok) {
-                    const int c = k / KHW;
-                    const int r = k - c * KHW;
-                    const int kh = r / s.KW, kw = r - kh * s.KW;
+            for (int e = 0; e < 8; ++e) ra[e] = ok ? __ldg(base + (size_t)(2 * e) * HW) : 0.f;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = k0 + kqa + 2 * e;
+                float a = 0.f;
+                if (k < K && m_ok) {
+                    const int tap = k / Csrc;
+                    const int c = k - tap * Csrc;
+                    const int kh = tap / s.KW, kw = tap - kh * s.KW;
                     const int hh = MODE == 0 ? h_l + kh - s.PH : h_l - kh + s.PH;
                     const int ww = MODE == 0 ? w_l + kw - s.PW : w_l - kw + s.PW;
                     if (hh >= 0 && hh < s.H && ww >= 0 && ww < s.W) a = __ldg(src_b + (size_t)c * HW + hh * s.W + ww);
                 }
-                if (n_ok) bv = __ldg(Wm + (size_t)k * N + gn_l);
+                ra[e] = a;
             }
-            ra[e] = a; rb[e] = bv;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k0 + kqb + 4 * e;
+            rb[e] = (k < K && n_ok) ? __ldg(Wm + (size_t)k * N + gn_l) : 0.f;
         }
     };
     fetch(0);
     for (int k0 = 0; k0 < K; k0 += CT_BK) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { As[kq + 4 * e][m_l] = ra[e]; Bs[kq + 4 * e][m_l] = rb[e]; }
+        for (int e = 0; e < 8; ++e) As[kqa + 2 * e][m_l] = ra[e];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Bs[kqb + 4 * e][n_l] = rb[e];
         __syncthreads();
         if (k0 + CT_BK < K) fetch(k0 + CT_BK);
 #pragma unroll
         for (int k = 0; k < CT_BK; ++k) {
-            float a[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[k][i * 16 + tm];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][tm * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + tm * 4]);
             const float4 bq = *reinterpret_cast<const float4*>(&Bs[k][tn * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + i * 16 + tm;
+    for (int half = 0; half < 2; ++half) {
+        const int m = m0 + half * 64 + tm * 4;            // 4 consecutive rows = 4 consecutive positions of one sample
         if (m >= M) continue;
         const int b = m / HW, hw = m - b * HW;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tn * 4 + j;
             if (n >= N) continue;
-            float v = acc[i][j];
-            if (MODE == 0 && bias) v += __ldg(bias + n);
-            dst[((size_t)b * N + n) * HW + hw] = v;
+            const float bv = (MODE == 0 && bias) ? __ldg(bias + n) : 0.f;
+            float* d = dst + ((size_t)b * N + n) * HW + hw;
+            if (m + 3 < M) {
+                *reinterpret_cast<float4*>(d) = make_float4(acc[half * 4][j] + bv, acc[half * 4 + 1][j] + bv, acc[half * 4 + 2][j] + bv,
+                                                            acc[half * 4 + 3][j] + bv);
+            } else {
+                for (int i = 0; i < 4 && m + i < M; ++i) d[i] = acc[half * 4 + i][j] + bv;
+            }
         }
     }
 }
@@ -178,10 +204,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const ConvG s, const fl
         if (t + 1 < n_tiles) fetch(t + 1);
 #pragma unroll
         for (int k = 0; k < CT_BK; ++k) {
-            float a[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[k][i * 16 + tm];
+            const float4 aq = *reinterpret_cast<const float4*>(&As[k][tm * 4]);
             const float4 bq = *reinterpret_cast<const float4*>(&Bs[k][tn * 4]);
+            const float a[4] = {aq.x, aq.y, aq.z, aq.w};
             const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -192,7 +217,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const ConvG s, const fl
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int m = m0 + i * 16 + tm;
+        const int m = m0 + tm * 4 + i;
         if (m >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -693,7 +718,7 @@ extern "C" int shm_cnn_train_forward(shm_cnn_trainer* h, const float* params, co
                                                                                            ws + h->wf[i], ws + h->wb[i]);
         SHM_LAUNCH_CHECK();
         const ConvG g = conv_g(b, B);
-        dim3 grid((unsigned)(((long long)B * b.H * b.W + CT_BM - 1) / CT_BM), (unsigned)((b.Cout + CT_BN - 1) / CT_BN));
+        dim3 grid((unsigned)(((long long)B * b.H * b.W + CI_BM - 1) / CI_BM), (unsigned)((b.Cout + CI_BN - 1) / CI_BN));
         conv_igemm_kernel<0><<<grid, 256, 0, st>>>(g, in, ws + h->wf[i], params + h->L.cb[i], ws + h->y[i]);
         SHM_LAUNCH_CHECK();
         const NormBlk k = norm_blk(h, params, i, B);
@@ -790,7 +815,7 @@ extern "C" int shm_cnn_train_backward(shm_cnn_trainer* h, const float* params, c
         conv_wgrad_kernel<<<gw, 256, 0, st>>>(g, ws + h->dy, xin, grads + L.cw[i], bps);
         SHM_LAUNCH_CHECK();
         if (i > 0) {
-            dim3 gd((unsigned)(((long long)B * b.H * b.W + CT_BM - 1) / CT_BM), (unsigned)((b.Cin + CT_BN - 1) / CT_BN));
+            dim3 gd((unsigned)(((long long)B * b.H * b.W + CI_BM - 1) / CI_BM), (unsigned)((b.Cin + CI_BN - 1) / CI_BN));
             conv_igemm_kernel<1><<<gd, 256, 0, st>>>(g, ws + h->dy, ws + h->wb[i], nullptr, ws + h->da);
             SHM_LAUNCH_CHECK();
             up = ws + h->da;
