@@ -225,6 +225,11 @@ def test_ddp_two_gpus_matches_single(tmp_path):
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
                             "127.0.0.1", "--master-port", str(port), str(script)], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout + r.stderr
+    # the collective itself: the all-reduced mean gradient of step 0 equals the full-batch gradient to fp32 summation noise
+    g1, g2 = np.load(tmp_path / "grad_w1.npy"), np.load(tmp_path / "grad_w2.npy")
+    assert np.max(np.abs(g1 - g2)) <= 2e-5 * np.max(np.abs(g1)), (np.max(np.abs(g1 - g2)), np.max(np.abs(g1)))
+    # parameters after two Adam steps: Adam divides by sqrt(v) ~ |g|, so entries whose gradient is summation noise move by
+    # +-lr with a noise-determined sign -- the bound is 2 steps x lr (+ clipping slack), the bulk agrees to 2e-5
     a, b = np.load(tmp_path / "flat_w1.npy"), np.load(tmp_path / "flat_w2.npy")
     assert np.mean(np.abs(a - b) <= 2e-5) > 0.99 and np.max(np.abs(a - b)) <= 3.1e-3
 
@@ -249,6 +254,8 @@ for step in range(2):
     X, eps = synth.windows(B, 100, 12, seed=10 + step), synth.eps(B, 16, seed=20 + step)
     lo, hi = rank * B // world, (rank + 1) * B // world
     tr.step(torch.from_numpy(X[lo:hi]).to(dev), 0.5, eps=torch.from_numpy(eps[lo:hi]).to(dev))
+    if step == 0 and rank == 0:
+        np.save(os.path.join(os.environ["OUT"], f"grad_w{world}.npy"), (tr.grads / world).cpu().numpy())     # SUM all-reduce -> mean
 torch.cuda.synchronize()
 if rank == 0:
     np.save(os.path.join(os.environ["OUT"], f"flat_w{world}.npy"), tr.flat.cpu().numpy())
