@@ -74,7 +74,7 @@ __device__ __forceinline__ void d2_epi_pass(const D2Ctx& cx, const float* bias_g
     const int wg = warp >> 2;                                  // units [8*wg, 8*wg+8) of each 32-unit chunk
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    for (int i = tid; i < D2_H * 4; i += TC_EPI_THREADS) cx.bias_s[i] = __ldg(bias_g + i);
+    for (int i = tid; i < D2_H * 4; i += TC_EPI_THREADS) cx.bias_s[i] = exp2f(fminf(__ldg(bias_g + i), 20.f));     // gate multiplier 2^bias (lstm_cell_bmul)
     epi_bar_sync();
     float cst[D2_NCH * D2_NT][TC_UPT];                         // cell state per virtual chunk, rotated so the next is cst[0]
 #pragma unroll
@@ -107,8 +107,8 @@ __device__ __forceinline__ void d2_epi_pass(const D2Ctx& cx, const float* bias_g
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const float4 bb = *reinterpret_cast<const float4*>(cx.bias_s + (u0 + u) * 4);
-                lstm_cell(__uint_as_float(g0[u]) + bb.x, __uint_as_float(g1[u]) + bb.y, __uint_as_float(g2[u]) + bb.z,
-                          __uint_as_float(g3[u]) + bb.w, cst[0][u], hv[u]);
+                lstm_cell_bmul(__uint_as_float(g0[u]), __uint_as_float(g1[u]), __uint_as_float(g2[u]), __uint_as_float(g3[u]), bb,
+                               cst[0][u], hv[u]);
             }
             const long long q3 = clock64();
             uint32_t hi[4], lo[4];
