@@ -207,9 +207,9 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& x, int c, uint32_t acc_p
     } else {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const float4 bb = *reinterpret_cast<const float4*>(x.bias_s + (u0 + u) * 4);
-            lstm_cell(__uint_as_float(g0[u]) + bb.x, __uint_as_float(g1[u]) + bb.y, __uint_as_float(g2[u]) + bb.z,
-                      __uint_as_float(g3[u]) + bb.w, cst[u], hv[u]);
+            const float4 bb = *reinterpret_cast<const float4*>(x.bias_s + (u0 + u) * 4);      // gate multipliers 2^bias
+            lstm_cell_bmul(__uint_as_float(g0[u]), __uint_as_float(g1[u]), __uint_as_float(g2[u]), __uint_as_float(g3[u]), bb, cst[u],
+                           hv[u]);
         }
     }
     uint32_t hi[4], lo[4];
@@ -255,7 +255,9 @@ __device__ __forceinline__ void epi_pass(const PassCtx& pc, const VaeDev& P, con
     const int row = (warp & 3) * 32 + lane;                    // TMEM lane == window row
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int T = pc.T;
-    for (int i = tid; i < H * 4; i += TC_EPI_THREADS) pc.bias_s[i] = __ldg(bias_g + i);
+    // non-hoisted passes fold the bias into the cell update as a multiplier 2^bias (lstm_cell_bmul); the hoisted pass reads b from G
+    if (!HOIST)
+        for (int i = tid; i < H * 4; i += TC_EPI_THREADS) pc.bias_s[i] = exp2f(fminf(__ldg(bias_g + i), 20.f));
     epi_bar_sync();
     float cst[NCH][TC_UPT];
 #pragma unroll
