@@ -69,6 +69,8 @@ __device__ __forceinline__ float silu_fast(float x) {
     return x * r;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ long long eff_windows(long long n_total, const int* n_dev, long long base, long long n_chunk) {
     long long e = n_total;
     if (n_dev) e = min(e, (long long)__ldg(n_dev));
@@ -225,7 +227,9 @@ __global__ void __launch_bounds__(256) ol_act_stage_kernel(const float* __restri
 // implicit-GEMM convolution of block L on the tensor cores
 // ------------------------------------------------------------------------------------------------------------
 struct OlGemmArgs {
-    const unsigned char* staged;
+    const unsigned char* staged;   // pre-staged operand images (separate staging kernel) ...
+    const float* prev;             // ... or the previous block's raw output + its GroupNorm scale / shift (fused staging)
+    const float2* scsh;
     const unsigned char* wimg;
     const float* bias;
     const float* wsc;          // [2]: weight scale, 1/scale
@@ -239,11 +243,16 @@ template <int L> struct OlBars {
     uint64_t a_landed[2], a_full[2], a_empty[2], b_full[OlDer<L>::NB], b_empty[OlDer<L>::NB], acc_full[2], acc_empty[2];
 };
 
-template <int L>
-__global__ void __launch_bounds__(256, 1) ol_conv_gemm_kernel(const OlGemmArgs a) {
+// NPW = 0: the A stages are bulk copies of images written by ol_act_stage_kernel (warps 4 + 7).
+// NPW > 0: NPW extra warps (8 ..) build the stages themselves from the previous block's raw fp32 output -- GroupNorm affine,
+// SiLU, MaxPool(2,1), fp16 hi/lo split, the three sensor-shifted copies -- so the activations make ONE trip through HBM per block
+// (raw write by the epilogue, raw read here) instead of three (raw write, raw read + image write, image read).
+template <int L, int NPW>
+__global__ void __launch_bounds__(256 + 32 * NPW, 1) ol_conv_gemm_kernel(const OlGemmArgs a) {
     using G = OlGeo<L>;
     using D = OlDer<L>;
     constexpr int NOUT = G::NOUT, KT = G::KT, RPH = G::RPH, HIN = G::HIN;
+    constexpr bool FUSED = NPW > 0;
     constexpr int NTAP = KT * 3;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* As = smem;
@@ -258,19 +267,117 @@ __global__ void __launch_bounds__(256, 1) ol_conv_gemm_kernel(const OlGemmArgs a
     const long long items = groups * D::NPAIR;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars->a_landed[i], 1); mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->a_landed[i], 1); mbar_init(&bars->a_full[i], FUSED ? NPW : 1); mbar_init(&bars->a_empty[i], 1); }
         for (int i = 0; i < D::NB; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
         fence_mbar_init();
     }
-    for (int i = tid; i < NOUT; i += 256) bias_s[i] = __ldg(a.bias + i);
+    for (int i = tid; i < NOUT; i += 256 + 32 * NPW) bias_s[i] = __ldg(a.bias + i);
     if (warp == 6) tmem_alloc(tmem_holder, D::TCOLS);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = *tmem_holder;
 
-    if (warp == 4) {                                   // ---- producer: A stages (one per item x ci-chunk)
+    if (FUSED && warp >= 8) {                          // ---- fused producer: A stages built from the raw activations
+        // Thread = one (k-core block of 8 channels, window, sensor column) for every NPT/2-th staged row: its NIT items differ only
+        // in the time step, so the 8 (scale, shift) pairs are loaded once per stage.  A warp's 32 lanes are 32 consecutive rows.
+        constexpr int NPT = (NPW > 0 ? NPW : 4) * 32, RS = NPT / 2, NIT = (D::R + RS - 1) / RS, PT = KT / 2;
+        constexpr uint32_t KB = D::R * 16;
+        static_assert(RS % RPH == 0 && D::R % 32 == 0, "rows of one thread share (window, column); whole warps per k-core block");
+        const int pt = tid - 256;
+        const int kc = pt / RS, rsub = pt - kc * RS;
+        const int wi = (rsub % RPH) >> 2, ws = rsub & 3;
+        const uint32_t so0 = (uint32_t)kc * KB + (uint32_t)rsub * 16u;              // byte offset of (kc, row rsub) inside an image
+        uint32_t it = 0;
+        for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+            const long long g = item / D::NPAIR;
+            const int p = (int)(item - g * D::NPAIR);
+            const long long win = g * D::WPT + wi;
+            const bool wok = win < n_eff;
+            const int h0 = p * D::PH + rsub / RPH - PT;                            // time step of item j: h0 + j * (RS / RPH)
+            const float* pa = a.prev + (((size_t)(wok ? win : 0) * (2 * HIN)) * 4 + ws) * G::CIN + kc * 8;
+            const float4* sp0 = reinterpret_cast<const float4*>(a.scsh + (wok ? win : 0) * 256 + kc * 8);
+            for (int cc = 0; cc < D::NCC; ++cc, ++it) {
+                const uint32_t s = it & 1;
+                float4 ra[NIT][4];                                 // two pooled time steps x 8 channels
+                bool ok[NIT];
+#pragma unroll
+                for (int j = 0; j < NIT; ++j) {
+                    const int h = h0 + j * (RS / RPH);
+                    ok[j] = wok && (rsub + j * RS < D::R) && h >= 0 && h < HIN;
+                    if (ok[j]) {
+                        const float4* q = reinterpret_cast<const float4*>(pa + (size_t)(2 * h) * 4 * G::CIN + cc * 16);
+                        ra[j][0] = __ldg(q); ra[j][1] = __ldg(q + 1);
+                        ra[j][2] = __ldg(q + G::CIN); ra[j][3] = __ldg(q + G::CIN + 1);       // + 4 sensor columns = next time step
+                    }
+                }
+                const float4 s01 = __ldg(sp0 + cc * 8), s23 = __ldg(sp0 + cc * 8 + 1), s45 = __ldg(sp0 + cc * 8 + 2), s67 = __ldg(sp0 + cc * 8 + 3);
+                // the NEXT stage's activations are pulled from DRAM into L2 while this one is computed (no registers held)
+                {
+                    const bool same = cc + 1 < D::NCC;
+                    const long long item2 = item + gridDim.x;
+                    if (same || item2 < items) {
+                        const long long g2 = item2 / D::NPAIR;
+                        const int p2 = (int)(item2 - g2 * D::NPAIR);
+                        const long long win2 = same ? win : g2 * D::WPT + wi;
+                        const int h02 = same ? h0 : p2 * D::PH + rsub / RPH - PT;
+                        const float* pn = a.prev + (((size_t)win2 * (2 * HIN)) * 4 + ws) * G::CIN + kc * 8 + (same ? (cc + 1) * 16 : 0);
+#pragma unroll
+                        for (int j = 0; j < NIT; ++j) {
+                            const int h = h02 + j * (RS / RPH);
+                            if (win2 < n_eff && (rsub + j * RS < D::R) && h >= 0 && h < HIN) {
+                                prefetch_l2(pn + (size_t)(2 * h) * 4 * G::CIN); prefetch_l2(pn + (size_t)(2 * h + 1) * 4 * G::CIN);
+                            }
+                        }
+                    }
+                }
+                // values first, slot second: the stage is computed into registers while the MMAs still read the slot it will go to
+                uint4 vh[NIT], vl[NIT];
+#pragma unroll
+                for (int j = 0; j < NIT; ++j) {
+                    uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+                    if (ok[j]) {
+                        float v[8];
+                        const float4 x0 = ra[j][0], x1 = ra[j][2], y0 = ra[j][1], y1 = ra[j][3];
+                        v[0] = fmaxf(silu_fast(fmaf(x0.x, s01.x, s01.y)), silu_fast(fmaf(x1.x, s01.x, s01.y)));
+                        v[1] = fmaxf(silu_fast(fmaf(x0.y, s01.z, s01.w)), silu_fast(fmaf(x1.y, s01.z, s01.w)));
+                        v[2] = fmaxf(silu_fast(fmaf(x0.z, s23.x, s23.y)), silu_fast(fmaf(x1.z, s23.x, s23.y)));
+                        v[3] = fmaxf(silu_fast(fmaf(x0.w, s23.z, s23.w)), silu_fast(fmaf(x1.w, s23.z, s23.w)));
+                        v[4] = fmaxf(silu_fast(fmaf(y0.x, s45.x, s45.y)), silu_fast(fmaf(y1.x, s45.x, s45.y)));
+                        v[5] = fmaxf(silu_fast(fmaf(y0.y, s45.z, s45.w)), silu_fast(fmaf(y1.y, s45.z, s45.w)));
+                        v[6] = fmaxf(silu_fast(fmaf(y0.z, s67.x, s67.y)), silu_fast(fmaf(y1.z, s67.x, s67.y)));
+                        v[7] = fmaxf(silu_fast(fmaf(y0.w, s67.z, s67.w)), silu_fast(fmaf(y1.w, s67.z, s67.w)));
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) split_f16x2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
+                    }
+                    vh[j] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    vl[j] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                mbar_wait(&bars->a_empty[s], ((it >> 1) & 1) ^ 1);
+                unsigned char* sbase = As + s * D::A_STAGE + so0;
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int j = 0; j < NIT; ++j) {
+                    if (rsub + j * RS >= D::R) continue;
+                    unsigned char* q1 = sbase + j * (RS * 16);
+                    // df = 1: in[w] at its own row.  df = 0 holds in[w-1]: this value lands one row down, and the quad's last lane
+                    // writes the zero of the w = 0 row instead; df = 2 (in[w+1]) mirrors it -- one store per image and thread.
+                    *reinterpret_cast<uint4*>(q1 + 2 * D::A_IMG) = vh[j];
+                    *reinterpret_cast<uint4*>(q1 + 3 * D::A_IMG) = vl[j];
+                    unsigned char* q0 = q1 + (ws != 3 ? 16 : -48);
+                    *reinterpret_cast<uint4*>(q0) = ws != 3 ? vh[j] : z;
+                    *reinterpret_cast<uint4*>(q0 + D::A_IMG) = ws != 3 ? vl[j] : z;
+                    unsigned char* q2 = q1 + 4 * D::A_IMG + (ws != 0 ? -16 : 48);
+                    *reinterpret_cast<uint4*>(q2) = ws != 0 ? vh[j] : z;
+                    *reinterpret_cast<uint4*>(q2 + D::A_IMG) = ws != 0 ? vl[j] : z;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a_full[s]);
+            }
+        }
+    } else if (!FUSED && warp == 4) {                  // ---- producer: A stages (one per item x ci-chunk)
         if (lane == 0) {
             uint32_t it = 0;
             for (long long item = blockIdx.x; item < items; item += gridDim.x) {
@@ -296,7 +403,7 @@ __global__ void __launch_bounds__(256, 1) ol_conv_gemm_kernel(const OlGemmArgs a
                 }
             }
         }
-    } else if (warp == 7) {                            // ---- fix-up: zero fill of the shifted copies' out-of-range column
+    } else if (!FUSED && warp == 7) {                  // ---- fix-up: zero fill of the shifted copies' out-of-range column
         uint32_t it = 0;
         constexpr uint32_t KB = D::R * 16;
         for (long long item = blockIdx.x; item < items; item += gridDim.x) {
@@ -558,20 +665,31 @@ static_assert((size_t)OlDer<1>::NPAIR * OlDer<1>::NCC * OlDer<1>::A_GSTAGE / OlD
 static_assert((size_t)OlDer<2>::NPAIR * OlDer<2>::NCC * OlDer<2>::A_GSTAGE / OlDer<2>::WPT <= kStagedPerWindow, "staged size");
 static_assert((size_t)OlDer<3>::NPAIR * OlDer<3>::NCC * OlDer<3>::A_GSTAGE / OlDer<3>::WPT <= kStagedPerWindow, "staged size");
 
+template <int L, int NPW>
+int launch_gemm(CnnOlTc* t, const OlGemmArgs& a, long long n_chunk, cudaStream_t st) {
+    using D = OlDer<L>;
+    SHM_CUDA(cudaFuncSetAttribute(ol_conv_gemm_kernel<L, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::SMEM));
+    const long long max_items = (n_chunk + D::WPT - 1) / D::WPT * D::NPAIR;
+    const int grid = (int)(max_items < t->nsm ? max_items : t->nsm);
+    ol_conv_gemm_kernel<L, NPW><<<grid, 256 + 32 * NPW, D::SMEM, st>>>(a);
+    SHM_LAUNCH_CHECK();
+    return SHM_OK;
+}
+
+constexpr int kOlProducerWarps = 8;
+
 template <int L>
 int run_block(CnnOlTc* t, const float* prev, float* out, const float* bias, const int* n_dev, long long n_total, long long base,
               long long n_chunk, cudaStream_t st) {
-    using D = OlDer<L>;
-    ol_act_stage_kernel<L><<<t->nsm * 8, 256, 0, st>>>(prev, t->scsh, n_dev, n_total, base, n_chunk, t->staged);
-    SHM_LAUNCH_CHECK();
-    OlGemmArgs a{t->staged, t->wimg[L - 1], bias, t->wscale + 2 * (L - 1), out, t->stats + (size_t)L * t->chunk * 16,
+    static const bool separate = [] { const char* e = getenv("SHM_OL_SEPARATE_STAGING"); return e && e[0] == '1'; }();
+    OlGemmArgs a{t->staged, prev, t->scsh, t->wimg[L - 1], bias, t->wscale + 2 * (L - 1), out, t->stats + (size_t)L * t->chunk * 16,
                  n_dev, n_total, base, n_chunk};
-    SHM_CUDA(cudaFuncSetAttribute(ol_conv_gemm_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::SMEM));
-    const long long max_items = (n_chunk + D::WPT - 1) / D::WPT * D::NPAIR;
-    const int grid = (int)(max_items < t->nsm ? max_items : t->nsm);
-    ol_conv_gemm_kernel<L><<<grid, 256, D::SMEM, st>>>(a);
-    SHM_LAUNCH_CHECK();
-    return SHM_OK;
+    if (separate) {
+        ol_act_stage_kernel<L><<<t->nsm * 8, 256, 0, st>>>(prev, t->scsh, n_dev, n_total, base, n_chunk, t->staged);
+        SHM_LAUNCH_CHECK();
+        return launch_gemm<L, 0>(t, a, n_chunk, st);
+    }
+    return launch_gemm<L, kOlProducerWarps>(t, a, n_chunk, st);
 }
 
 }  // namespace
