@@ -49,7 +49,7 @@ template <int L> struct OlDer {
     static constexpr int TG = (G::NOUT <= 64) ? 3 : 1;     // taps per weight stage (small-N MMAs are short: fewer barrier round trips)
     static constexpr int B_TAP = G::NOUT * 64;             // {hi, lo} x [NOUT x 16] fp16 of one tap
     static constexpr int B_STAGE = TG * B_TAP;
-    static constexpr int NB = 4;                           // weight ring stages
+    static constexpr int NB = 4;                           // weight ring stages (8 measured slower: the shared memory it takes is L1 the fused producer's loads need)
     static constexpr int NACC = (4 * G::NOUT <= 512) ? 2 : 1;   // accumulator sets (pair = 2*NOUT columns): double buffered when TMEM allows
     static constexpr int OFF_BAR = 2 * A_STAGE + NB * B_STAGE;
     static constexpr int OFF_BIAS = OFF_BAR + 256;         // fp32 bias[NOUT]
@@ -242,6 +242,7 @@ struct OlGemmArgs {
 template <int L> struct OlBars {
     uint64_t a_landed[2], a_full[2], a_empty[2], b_full[OlDer<L>::NB], b_empty[OlDer<L>::NB], acc_full[2], acc_empty[2];
 };
+static_assert(sizeof(OlBars<1>) <= 240 && sizeof(OlBars<3>) <= 240, "barriers, then the TMEM base word at +240");
 
 // NPW = 0: the A stages are bulk copies of images written by ol_act_stage_kernel (warps 4 + 7).
 // NPW > 0: NPW extra warps (8 ..) build the stages themselves from the previous block's raw fp32 output -- GroupNorm affine,
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(256 + 32 * NPW, 1) ol_conv_gemm_kernel(const O
     unsigned char* As = smem;
     unsigned char* Bs = smem + 2 * D::A_STAGE;
     OlBars<L>* bars = reinterpret_cast<OlBars<L>*>(smem + D::OFF_BAR);
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + D::OFF_BAR + 192);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + D::OFF_BAR + 240);
     float* bias_s = reinterpret_cast<float*>(smem + D::OFF_BIAS);
     double* red_s = reinterpret_cast<double*>(smem + D::OFF_RED);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -500,16 +501,26 @@ __global__ void __launch_bounds__(256 + 32 * NPW, 1) ol_conv_gemm_kernel(const O
             for (int i = 0; i < 8; ++i) { gs[i] = 0.f; gq[i] = 0.f; }
             mbar_wait(&bars->acc_full[ab_set], (n_item / D::NACC) & 1);
             tc_fence_after_sync();
+            // the accumulator is drained in 32-column chunks with the NEXT chunk's TMEM load in flight under the current chunk's
+            // stores and statistics (two register buffers): with one accumulator set (block 4) the MMA issuer waits for this drain
+            constexpr int NCK = NOUT / 32;
+            static_assert(NCK % 2 == 0, "chunk 0 of the second tile lands in buffer A again");
+            const uint32_t acc0 = tbase + lane_base + (uint32_t)(ab_set * 2 * NOUT);
+            uint32_t va[32], vb[32];
+            tmem_ld32(acc0, va);
 #pragma unroll 1
             for (int tile = 0; tile < 2; ++tile) {
                 const int h = p * D::PH + tile * D::HT + row / RPH;
                 const bool valid = h < HIN && win < n_eff;
                 float* orow = a.out + (((size_t)(valid ? win : 0) * HIN + (valid ? h : 0)) * 4 + w) * NOUT;
 #pragma unroll
-                for (int c0 = 0; c0 < NOUT; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tbase + lane_base + (uint32_t)((ab_set * 2 + tile) * NOUT + c0), v);
+                for (int ci = 0; ci < NCK; ++ci) {
+                    const int c0 = ci * 32;
                     tmem_ld_wait();
+                    uint32_t (&v)[32] = (ci & 1) ? vb : va;
+                    uint32_t (&vn)[32] = (ci & 1) ? va : vb;
+                    if (ci + 1 < NCK) tmem_ld32(acc0 + (uint32_t)(tile * NOUT + c0 + 32), vn);
+                    else if (tile == 0) tmem_ld32(acc0 + (uint32_t)NOUT, vn);
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), inv, bias_s[c0 + j]);
