@@ -689,10 +689,17 @@ int launch_gemm(CnnOlTc* t, const OlGemmArgs& a, long long n_chunk, cudaStream_t
 
 constexpr int kOlProducerWarps = 8;
 
+// SHM_OL_SEPARATE_STAGING=1 selects the round-1 structure (ol_act_stage_kernel writes the operand images to HBM, the GEMM's producer
+// bulk-copies them): kept as the A/B reference of the fused producer (4.58 vs 3.90 ms per 8192 windows), not a fallback
+bool ol_separate_staging() {
+    static const bool separate = [] { const char* e = getenv("SHM_OL_SEPARATE_STAGING"); return e && e[0] == '1'; }();
+    return separate;
+}
+
 template <int L>
 int run_block(CnnOlTc* t, const float* prev, float* out, const float* bias, const int* n_dev, long long n_total, long long base,
               long long n_chunk, cudaStream_t st) {
-    static const bool separate = [] { const char* e = getenv("SHM_OL_SEPARATE_STAGING"); return e && e[0] == '1'; }();
+    const bool separate = ol_separate_staging();
     OlGemmArgs a{t->staged, prev, t->scsh, t->wimg[L - 1], bias, t->wscale + 2 * (L - 1), out, t->stats + (size_t)L * t->chunk * 16,
                  n_dev, n_total, base, n_chunk};
     if (separate) {
@@ -744,11 +751,11 @@ static int ensure_workspace(CnnOlTc* t, long long n) {
     long long want = n < kMaxChunk ? n : kMaxChunk;
     want = (want + 255) / 256 * 256;
     if (t->chunk >= want) return SHM_OK;
-    if (t->raw[0]) { cudaFree(t->raw[0]); cudaFree(t->raw[1]); cudaFree(t->staged); cudaFree(t->stats); cudaFree(t->scsh); }
+    if (t->raw[0]) { cudaFree(t->raw[0]); cudaFree(t->raw[1]); if (t->staged) cudaFree(t->staged); cudaFree(t->stats); cudaFree(t->scsh); }
     t->raw[0] = t->raw[1] = nullptr; t->staged = nullptr; t->stats = nullptr; t->scsh = nullptr; t->chunk = 0;
     const size_t raw_bytes = (size_t)want * 25600 * sizeof(float);
     if (cudaMalloc(&t->raw[0], raw_bytes) != cudaSuccess || cudaMalloc(&t->raw[1], raw_bytes) != cudaSuccess ||
-        cudaMalloc(&t->staged, (size_t)want * kStagedPerWindow) != cudaSuccess ||
+        (ol_separate_staging() && cudaMalloc(&t->staged, (size_t)want * kStagedPerWindow) != cudaSuccess) ||
         cudaMalloc(&t->stats, (size_t)4 * want * 16 * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&t->scsh, (size_t)want * 256 * sizeof(float2)) != cudaSuccess) {
         set_cuda_error(cudaGetLastError(), "cudaMalloc(cnnol tensor-core workspace)");

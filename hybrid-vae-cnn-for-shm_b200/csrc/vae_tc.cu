@@ -131,6 +131,37 @@ __device__ __forceinline__ void lstm_cell_bmul(float ai, float af, float ag, flo
     h = (2.f - q) * rcp_approx(fmaf(eo, B.w, 1.f) * q);
 }
 
+// Two cells at once on the packed fp32 pipe (sm_100 fma/mul/add.f32x2 -> FFMA2: two lanes per issue slot, same flops per clock as
+// two FFMAs -- scripts/ffma2_probe.cu): the cell update's 16 FMA-pipe instructions per cell become 15 per PAIR, which frees ~8 of
+// ~35 issue slots per cell next to the 7 MUFU operations that bound it.  Same formulas as lstm_cell_bmul (n = 2 - d as in lstm_cell).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 ex2_2(float x0, float x1, float clampv) {
+    return pk2(ex2_approx(fminf(x0, clampv)), ex2_approx(fminf(x1, clampv)));
+}
+__device__ __forceinline__ f32x2 rcp_2(f32x2 v) { float a, b; unpk2(v, a, b); return pk2(rcp_approx(a), rcp_approx(b)); }
+// gate arguments of units (u, u+1); B4 = multipliers {Bi(u),Bi(u+1)}, {Bf..}, {Bg..}, {Bo..}; c, h in/out for both units
+__device__ __forceinline__ void lstm_cell_bmul2(float ai0, float ai1, float af0, float af1, float ag0, float ag1, float ao0, float ao1,
+                                                const f32x2 (&B4)[4], float& c0, float& c1, float& h0, float& h1) {
+    const f32x2 one = pk2(1.f, 1.f), two = pk2(2.f, 2.f), m1 = pk2(-1.f, -1.f), k2 = pk2(2.f * NLOG2E, 2.f * NLOG2E);
+    const f32x2 ei = ex2_2(ai0, ai1, 22.f), ef = ex2_2(af0, af1, 22.f), eg = ex2_2(ag0, ag1, 22.f), eo = ex2_2(ao0, ao1, 22.f);
+    const f32x2 a = fma2(ei, B4[0], one), b = fma2(ef, B4[1], one), d = fma2(eg, B4[2], one);
+    const f32x2 n = fma2(d, m1, two);
+    const f32x2 P = mul2(a, d);
+    const f32x2 num = fma2(pk2(c0, c1), P, mul2(n, b));
+    const f32x2 c = mul2(num, rcp_2(mul2(P, b)));
+    unpk2(c, c0, c1);
+    float k0, k1;
+    unpk2(mul2(c, k2), k0, k1);
+    const f32x2 q = add2(ex2_2(k0, k1, 30.f), one);
+    const f32x2 h = mul2(fma2(q, m1, two), rcp_2(mul2(fma2(eo, B4[3], one), q)));
+    unpk2(h, h0, h1);
+}
+
 // optional role profiling (TcDev.dbg != nullptr): cycles the MMA issuer spends in each kind of wait
 #define TC_TWAIT(slot, bar, par)                                   \
     do {                                                           \

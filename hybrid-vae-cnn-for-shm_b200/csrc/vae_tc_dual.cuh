@@ -74,7 +74,11 @@ __device__ __forceinline__ void d2_epi_pass(const D2Ctx& cx, const float* bias_g
     const int wg = warp >> 2;                                  // units [8*wg, 8*wg+8) of each 32-unit chunk
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    for (int i = tid; i < D2_H * 4; i += TC_EPI_THREADS) cx.bias_s[i] = exp2f(fminf(__ldg(bias_g + i), 20.f));     // gate multiplier 2^bias (lstm_cell_bmul)
+    // gate multipliers 2^bias (lstm_cell_bmul2), stored per unit PAIR as {Bi(u),Bi(u+1)} {Bf..} {Bg..} {Bo..}
+    for (int i = tid; i < D2_H * 4; i += TC_EPI_THREADS) {
+        const int unit = i >> 2, gate = i & 3;
+        cx.bias_s[(unit >> 1) * 8 + gate * 2 + (unit & 1)] = exp2f(fminf(__ldg(bias_g + i), 20.f));
+    }
     epi_bar_sync();
     float cst[D2_NCH * D2_NT][TC_UPT];                         // cell state per virtual chunk, rotated so the next is cst[0]
 #pragma unroll
@@ -105,10 +109,13 @@ __device__ __forceinline__ void d2_epi_pass(const D2Ctx& cx, const float* bias_g
             if (lane == 0) mbar_arrive(&cx.bars->acc_empty[tl]);
             float hv[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float4 bb = *reinterpret_cast<const float4*>(cx.bias_s + (u0 + u) * 4);
-                lstm_cell_bmul(__uint_as_float(g0[u]), __uint_as_float(g1[u]), __uint_as_float(g2[u]), __uint_as_float(g3[u]), bb,
-                               cst[0][u], hv[u]);
+            for (int u = 0; u < 8; u += 2) {
+                const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(cx.bias_s + (u0 + u) * 4);
+                const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(cx.bias_s + (u0 + u) * 4 + 4);
+                const f32x2 B4[4] = {b01.x, b01.y, b23.x, b23.y};
+                lstm_cell_bmul2(__uint_as_float(g0[u]), __uint_as_float(g0[u + 1]), __uint_as_float(g1[u]), __uint_as_float(g1[u + 1]),
+                                __uint_as_float(g2[u]), __uint_as_float(g2[u + 1]), __uint_as_float(g3[u]), __uint_as_float(g3[u + 1]), B4,
+                                cst[0][u], cst[0][u + 1], hv[u], hv[u + 1]);
             }
             const long long q3 = clock64();
             uint32_t hi[4], lo[4];
