@@ -98,42 +98,18 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 // LSTM cell from pre-scaled gate arguments (ai = -log2e*a_i, af, ao likewise, ag = -2log2e*a_g):
 // sigma(a) = 1/(1+2^ai), tanh(a) = (1-2^ag)/(1+2^ag); the three divisions of c' = f*c + i*g share one
 // reciprocal, the two of h = o*tanh(c') another: 5 ex2 + 2 rcp per cell.
-__device__ __forceinline__ void lstm_cell(float ai, float af, float ag, float ao, float& c, float& h) {
-    const float ei = ex2_approx(fminf(ai, 30.f));
-    const float ef = ex2_approx(fminf(af, 30.f));
-    const float eg = ex2_approx(fminf(ag, 30.f));
-    const float eo = ex2_approx(fminf(ao, 30.f));
-    const float a = 1.f + ei, b = 1.f + ef, d = 1.f + eg, n = 2.f - d;
-    const float P = a * d;
-    const float num = fmaf(c, P, n * b);
-    c = num * rcp_approx(P * b);
-    const float ec = ex2_approx(fminf(c * (2.f * NLOG2E), 30.f));
-    const float q = 1.f + ec;
-    h = (2.f - q) * rcp_approx((1.f + eo) * q);
-}
-
-// Same cell with the (pre-scaled) bias folded into a per-gate MULTIPLIER B = 2^bias: 2^(a + bias) = 2^a * B, so `1 + e` becomes one
-// FMA and the four bias additions disappear (-4 of ~30 ALU instructions per cell).  The two-tile H = 64 scorer is bound by issue
-// slots (74 % busy next to XU 70 %); moving a reciprocal onto the FMA pipe instead made it slower (76.8 vs 74.4 ms per 2^20 windows).
-__device__ __forceinline__ void lstm_cell_bmul(float ai, float af, float ag, float ao, float4 B, float& c, float& h) {
-    // arguments clamped at 22 and multipliers at 2^20 (by the caller): 1 + e*B <= 2^42, so P*b <= 2^126 stays finite when three
-    // gates saturate at once; the saturation floor 2^-22 is below what the 1e-4 score tolerance can see
-    const float ei = ex2_approx(fminf(ai, 22.f));
-    const float ef = ex2_approx(fminf(af, 22.f));
-    const float eg = ex2_approx(fminf(ag, 22.f));
-    const float eo = ex2_approx(fminf(ao, 22.f));
-    const float a = fmaf(ei, B.x, 1.f), b = fmaf(ef, B.y, 1.f), d = fmaf(eg, B.z, 1.f), n = fmaf(-eg, B.z, 1.f);
-    const float P = a * d;
-    const float num = fmaf(c, P, n * b);
-    c = num * rcp_approx(P * b);
-    const float ec = ex2_approx(fminf(c * (2.f * NLOG2E), 30.f));
-    const float q = 1.f + ec;
-    h = (2.f - q) * rcp_approx(fmaf(eo, B.w, 1.f) * q);
-}
-
+//   e_x = 2^min(a_x, clamp);  a = 1+e_i, b = 1+e_f, d = 1+e_g, n = 2-d;  P = a*d;  c' = (c*P + n*b) / (P*b);
+//   q = 1 + 2^min(2*NLOG2E*c', 30);  h = (2-q) / ((1+e_o)*q)
+// Where a pass adds the same bias for every window (all but the hoisted decoder pass) the pre-scaled bias is folded into a per-gate
+// MULTIPLIER B = 2^bias: 2^(a + bias) = 2^a * B, so `1 + e` becomes one FMA and the four bias additions disappear.  Arguments are
+// then clamped at 22 and multipliers at 2^20 (by the caller): 1 + e*B <= 2^42, so P*b <= 2^126 stays finite when three gates
+// saturate at once; the saturation floor 2^-22 is below what the 1e-4 score tolerance can see.  The two-tile H = 64 scorer is bound
+// by issue slots (74 % busy next to XU 70 %); moving a reciprocal onto the FMA pipe instead made it slower (76.8 vs 74.4 ms per 2^20
+// windows), the multiplier gained 3 % and the packed pair update below another 3 %.
+//
 // Two cells at once on the packed fp32 pipe (sm_100 fma/mul/add.f32x2 -> FFMA2: two lanes per issue slot, same flops per clock as
 // two FFMAs -- scripts/ffma2_probe.cu): the cell update's 16 FMA-pipe instructions per cell become 15 per PAIR, which frees ~8 of
-// ~35 issue slots per cell next to the 7 MUFU operations that bound it.  Same formulas as lstm_cell_bmul (n = 2 - d as in lstm_cell).
+// ~35 issue slots per cell next to the 7 MUFU operations that bound it.
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
@@ -162,6 +138,25 @@ __device__ __forceinline__ void lstm_cell_bmul2(float ai0, float ai1, float af0,
     unpk2(h, h0, h1);
 }
 
+// The same pair update from complete gate arguments (bias already inside, as in the hoisted decoder pass): lstm_cell's formulas.
+__device__ __forceinline__ void lstm_cell2(f32x2 ai, f32x2 af, f32x2 ag, f32x2 ao, float& c0, float& c1, float& h0, float& h1) {
+    const f32x2 one = pk2(1.f, 1.f), two = pk2(2.f, 2.f), m1 = pk2(-1.f, -1.f), k2 = pk2(2.f * NLOG2E, 2.f * NLOG2E);
+    float x0, x1;
+    unpk2(ai, x0, x1); const f32x2 a = add2(ex2_2(x0, x1, 30.f), one);
+    unpk2(af, x0, x1); const f32x2 b = add2(ex2_2(x0, x1, 30.f), one);
+    unpk2(ag, x0, x1); const f32x2 d = add2(ex2_2(x0, x1, 30.f), one);
+    unpk2(ao, x0, x1); const f32x2 o = add2(ex2_2(x0, x1, 30.f), one);
+    const f32x2 n = fma2(d, m1, two);
+    const f32x2 P = mul2(a, d);
+    const f32x2 num = fma2(pk2(c0, c1), P, mul2(n, b));
+    const f32x2 c = mul2(num, rcp_2(mul2(P, b)));
+    unpk2(c, c0, c1);
+    unpk2(mul2(c, k2), x0, x1);
+    const f32x2 q = add2(ex2_2(x0, x1, 30.f), one);
+    const f32x2 h = mul2(fma2(q, m1, two), rcp_2(mul2(o, q)));
+    unpk2(h, h0, h1);
+}
+
 // optional role profiling (TcDev.dbg != nullptr): cycles the MMA issuer spends in each kind of wait
 #define TC_TWAIT(slot, bar, par)                                   \
     do {                                                           \
@@ -186,7 +181,7 @@ struct EpiCtx {
     const float* bias_s;
     unsigned char* img;          // scratch image of this step (SINK_STREAM)
     float* hT;                   // fp32 h_T [H][128] (SINK_LAST_ENC)
-    const unsigned char* gs;     // input buffers carrying G chunk images [32 units][128 rows][4 gates] fp32 (HOIST)
+    const unsigned char* gs;     // input buffers carrying G chunk images [2 planes][16 unit pairs][128 rows][4] fp32 (HOIST)
     int wg, row, lane;
     bool last_step, first_step;
     long long* prof;
@@ -226,21 +221,27 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& x, int c, uint32_t acc_p
             for (int u = 0; u < 8; ++u) { g0[u] = 0u; g1[u] = 0u; g2[u] = 0u; g3[u] = 0u; }
         }
         mbar_wait(&x.bars->g_full[b], g_parity);                    // this chunk's G image has landed in input buffer b
-        const float4* G = reinterpret_cast<const float4*>(x.gs + b * S::IMG) + (x.wg * 8) * TCM + x.row;
+        // G = u W_ih^T + b per unit PAIR and row: plane 0 {i(u),i(u+1),f(u),f(u+1)}, plane 1 {g.., o..}, [plane][pair][row] 16 B each
+        const ulonglong2* G = reinterpret_cast<const ulonglong2*>(x.gs + b * S::IMG) + (x.wg * 4) * TCM + x.row;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const float4 bb = G[u * TCM];                            // u W_ih^T + b for (row, unit u0+u): gates i,f,g,o
-            lstm_cell(__uint_as_float(g0[u]) + bb.x, __uint_as_float(g1[u]) + bb.y, __uint_as_float(g2[u]) + bb.z,
-                      __uint_as_float(g3[u]) + bb.w, cst[u], hv[u]);
+        for (int u = 0; u < 8; u += 2) {
+            const ulonglong2 gif = G[(u >> 1) * TCM], ggo = G[(16 + (u >> 1)) * TCM];
+            lstm_cell2(add2(pk2(__uint_as_float(g0[u]), __uint_as_float(g0[u + 1])), gif.x),
+                       add2(pk2(__uint_as_float(g1[u]), __uint_as_float(g1[u + 1])), gif.y),
+                       add2(pk2(__uint_as_float(g2[u]), __uint_as_float(g2[u + 1])), ggo.x),
+                       add2(pk2(__uint_as_float(g3[u]), __uint_as_float(g3[u + 1])), ggo.y), cst[u], cst[u + 1], hv[u], hv[u + 1]);
         }
         __syncwarp();
         if (x.lane == 0) mbar_arrive(&x.bars->g_empty[b]);
     } else {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const float4 bb = *reinterpret_cast<const float4*>(x.bias_s + (u0 + u) * 4);      // gate multipliers 2^bias
-            lstm_cell_bmul(__uint_as_float(g0[u]), __uint_as_float(g1[u]), __uint_as_float(g2[u]), __uint_as_float(g3[u]), bb, cst[u],
-                           hv[u]);
+        for (int u = 0; u < 8; u += 2) {                                 // gate multipliers 2^bias, stored per unit pair
+            const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(x.bias_s + (u0 + u) * 4);
+            const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(x.bias_s + (u0 + u) * 4 + 4);
+            const f32x2 B4[4] = {b01.x, b01.y, b23.x, b23.y};
+            lstm_cell_bmul2(__uint_as_float(g0[u]), __uint_as_float(g0[u + 1]), __uint_as_float(g1[u]), __uint_as_float(g1[u + 1]),
+                            __uint_as_float(g2[u]), __uint_as_float(g2[u + 1]), __uint_as_float(g3[u]), __uint_as_float(g3[u + 1]), B4,
+                            cst[u], cst[u + 1], hv[u], hv[u + 1]);
         }
     }
     uint32_t hi[4], lo[4];
@@ -269,7 +270,7 @@ struct PassCtx {
     float* bo_s;
     unsigned char* scratch;
     float* heads_scratch;
-    unsigned char* gbuf;         // global image of G, [NCH][32 units][128 rows][4 gates] fp32 (IN_HOIST)
+    unsigned char* gbuf;         // global image of G, [NCH][2 planes][16 unit pairs][128 rows][4] fp32 (IN_HOIST)
     uint32_t t_acc, t_h;
     int T, nvalid, hT_buf, u_buf;
     long long n0;
@@ -288,7 +289,10 @@ __device__ __forceinline__ void epi_pass(const PassCtx& pc, const VaeDev& P, con
     const int T = pc.T;
     // non-hoisted passes fold the bias into the cell update as a multiplier 2^bias (lstm_cell_bmul); the hoisted pass reads b from G
     if (!HOIST)
-        for (int i = tid; i < H * 4; i += TC_EPI_THREADS) pc.bias_s[i] = exp2f(fminf(__ldg(bias_g + i), 20.f));
+        for (int i = tid; i < H * 4; i += TC_EPI_THREADS) {               // {Bi(u),Bi(u+1)} {Bf..} {Bg..} {Bo..} per unit pair (lstm_cell_bmul2)
+            const int unit = i >> 2, gate = i & 3;
+            pc.bias_s[(unit >> 1) * 8 + gate * 2 + (unit & 1)] = exp2f(fminf(__ldg(bias_g + i), 20.f));
+        }
     epi_bar_sync();
     float cst[NCH][TC_UPT];
 #pragma unroll
@@ -326,7 +330,8 @@ __device__ __forceinline__ void epi_pass(const PassCtx& pc, const VaeDev& P, con
 }
 
 // IN_HOIST, once per tile: drain G = u W_ih^T (+ b) chunk by chunk from the accumulators into the per-CTA global image
-// [chunk][32 units][128 rows][4 gates] fp32 -- the layout the cell update reads back from shared memory (one float4 per row and unit).
+// [chunk][2 planes][16 unit pairs][128 rows][4] fp32 -- the layout the packed cell update reads back from shared memory (two 16-byte
+// loads per row and unit pair: {i, i', f, f'} and {g, g', o, o'}).
 template <int H>
 __device__ __forceinline__ void epi_hoist_pre(const PassCtx& pc, const float* bias_g, Cnt2 acc_cnt) {
     using S = TcSmem<H>;
@@ -354,12 +359,15 @@ __device__ __forceinline__ void epi_hoist_pre(const PassCtx& pc, const float* bi
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&pc.bars->acc_empty[b]);
-        float4* G = reinterpret_cast<float4*>(pc.gbuf + (size_t)c * S::IMG) + (wg * 8) * TCM + row;
+        float4* G = reinterpret_cast<float4*>(pc.gbuf + (size_t)c * S::IMG) + (wg * 4) * TCM + row;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const float4 bb = *reinterpret_cast<const float4*>(pc.bias_s + (c * 32 + wg * 8 + u) * 4);
-            G[u * TCM] = make_float4(__uint_as_float(g0[u]) + bb.x, __uint_as_float(g1[u]) + bb.y, __uint_as_float(g2[u]) + bb.z,
-                                     __uint_as_float(g3[u]) + bb.w);
+        for (int u = 0; u < 8; u += 2) {                          // unit pairs: plane 0 = {i, i', f, f'}, plane 1 = {g, g', o, o'}
+            const float4 b0 = *reinterpret_cast<const float4*>(pc.bias_s + (c * 32 + wg * 8 + u) * 4);
+            const float4 b1 = *reinterpret_cast<const float4*>(pc.bias_s + (c * 32 + wg * 8 + u + 1) * 4);
+            G[(u >> 1) * TCM] = make_float4(__uint_as_float(g0[u]) + b0.x, __uint_as_float(g0[u + 1]) + b1.x,
+                                            __uint_as_float(g1[u]) + b0.y, __uint_as_float(g1[u + 1]) + b1.y);
+            G[(16 + (u >> 1)) * TCM] = make_float4(__uint_as_float(g2[u]) + b0.z, __uint_as_float(g2[u + 1]) + b1.z,
+                                                   __uint_as_float(g3[u]) + b0.w, __uint_as_float(g3[u + 1]) + b1.w);
         }
     }
     fence_proxy_async_all();                                   // the image is read back by bulk copies
