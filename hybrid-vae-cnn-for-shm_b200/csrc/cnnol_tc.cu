@@ -69,13 +69,6 @@ __device__ __forceinline__ float silu_fast(float x) {
     return x * r;
 }
 
-// packed fp32 pairs (sm_100 fma/add.f32x2 -> FFMA2 / FADD2: two lanes per issue slot; scripts/ffma2_probe.cu)
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ long long eff_windows(long long n_total, const int* n_dev, long long base, long long n_chunk) {
@@ -496,7 +489,6 @@ __global__ void __launch_bounds__(256 + 32 * NPW, 1) ol_conv_gemm_kernel(const O
         const int row = warp * 32 + lane;
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
         const float inv = __ldg(a.wsc + 1);
-        const f32x2 inv2 = pk2(inv, inv);
         const int wi = (row % RPH) >> 2, w = row & 3;
         uint32_t n_item = 0;
         for (long long item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
@@ -529,25 +521,20 @@ __global__ void __launch_bounds__(256 + 32 * NPW, 1) ol_conv_gemm_kernel(const O
                     uint32_t (&vn)[32] = (ci & 1) ? va : vb;
                     if (ci + 1 < NCK) tmem_ld32(acc0 + (uint32_t)(tile * NOUT + c0 + 32), vn);
                     else if (tile == 0) tmem_ld32(acc0 + (uint32_t)NOUT, vn);
-                    // channel PAIRS on the packed fp32 pipe (FFMA2 / FADD2): scale + bias, sum and sum of squares in half the issue slots
-                    f32x2 f2[16];
+                    float f[32];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(bias_s + c0 + 4 * j);
-                        f2[2 * j] = fma2(pk2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), inv2, bb.x);
-                        f2[2 * j + 1] = fma2(pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), inv2, bb.y);
-                    }
+                    for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), inv, bias_s[c0 + j]);
                     if (valid) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) *reinterpret_cast<ulonglong2*>(orow + c0 + 4 * q) = make_ulonglong2(f2[2 * q], f2[2 * q + 1]);
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4*>(orow + c0 + 4 * q) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
 #pragma unroll
                         for (int gg = 0; gg < GPC; ++gg) {
-                            f32x2 s1 = 0ull, q2 = 0ull;
+                            float s1 = 0.f, q2 = 0.f;
 #pragma unroll
-                            for (int j = 0; j < GS / 2 && j < 16; ++j) { const f32x2 x = f2[gg * (GS / 2) + j]; s1 = add2(s1, x); q2 = fma2(x, x, q2); }
-                            float lo, hi;
-                            unpk2(s1, lo, hi); gs[c0 / GS + gg] += lo + hi;
-                            unpk2(q2, lo, hi); gq[c0 / GS + gg] += lo + hi;
+                            for (int j = 0; j < GS && j < 32; ++j) { const float x = f[gg * GS + j]; s1 += x; q2 = fmaf(x, x, q2); }
+                            gs[c0 / GS + gg] += s1;
+                            gq[c0 / GS + gg] += q2;
                         }
                     }
                 }
