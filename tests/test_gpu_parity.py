@@ -245,6 +245,25 @@ def test_cnnol_ragged_idx_and_device_count(cuda_dev, engine):
         assert np.allclose(l2.cpu().numpy(), O.cnnol_forward(sd, xs[:, None].astype(np.float32)), rtol=REL_TOL, atol=LOGIT_ABS)
 
 
+def test_cnnol_two_chunks_position_independent(cuda_dev):
+    """Tensor-core openLAB CNN over more windows than one internal chunk (8192) with a ragged tail: a window's logits do not depend
+    on the chunk, tile pair or producer group it lands in (the fused operand producer stages 4 / 8 / 16 windows per tile) -- a
+    shuffled subset recomputed through a gather list agrees to fp32 rounding of the GroupNorm statistics, a handful with the oracle."""
+    sd = synth.cnnol_weights(seed=5)
+    N = 8192 + 37
+    x = synth.windows(N, 200, 4, seed=6, amp=1.5)
+    cnn = ops.CnnOpenLab(sd, cuda_dev)
+    src = ops.WindowSource(to_dev(x, cuda_dev), 200)
+    a = cnn.forward(src)
+    assert a.shape[0] == N and torch.isfinite(a).all()
+    sel = torch.cat([torch.tensor([0, 8191, 8192, N - 1]), torch.randperm(N)[:203]]).to(torch.int32).to(cuda_dev)
+    b = cnn.forward(src, n=int(sel.numel()), idx=sel)
+    assert torch.allclose(b, a[sel.long()], rtol=1e-5, atol=1e-6)
+    k = sel[:6].cpu().numpy()
+    ref = O.cnnol_forward(sd, x[k][:, None].astype(np.float32))
+    assert np.allclose(a[sel[:6].long()].cpu().numpy(), ref, rtol=REL_TOL, atol=LOGIT_ABS)
+
+
 @pytest.mark.parametrize("engine", engines())
 def test_openlab_hybrid_real_windows(cuda_dev, golden_dir, engine):
     g = np.load(golden_dir / "openlab_real_windows.npz")
