@@ -39,6 +39,12 @@ struct Cnn4Dev {
     const float *fc2w, *fc2b;
 };
 
+// packed fp32 pairs (sm_100 fma.rn.f32x2 -> FFMA2: two lanes per issue slot, same flops per clock; scripts/ffma2_probe.cu)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 __global__ void __launch_bounds__(C4_THREADS)
 cnn4dof_conv_kernel(Cnn4Dev P, const float* __restrict__ x, const int* __restrict__ n_dev, long long n,
                     float* __restrict__ feat) {
@@ -51,12 +57,20 @@ cnn4dof_conv_kernel(Cnn4Dev P, const float* __restrict__ x, const int* __restric
     long long n_eff = n;
     if (n_dev) n_eff = min(n_eff, (long long)__ldg(n_dev));
 
-    for (int i = tid; i < C4_C1 * 2 * 9; i += C4_THREADS) sw1[i] = __ldg(P.w1 + i);
-    for (int i = tid; i < C4_C2 * C4_C1 * 9; i += C4_THREADS) sw2[i] = __ldg(P.w2 + i);
+    // weights staged as [input channel][tap][output channel]: the 8 output channels of an item are two 16-byte loads per tap, and
+    // adjacent channels are the two halves of a packed-FMA operand (fma.rn.f32x2 -> FFMA2, two channels per issue slot)
+    for (int i = tid; i < C4_C1 * 2 * 9; i += C4_THREADS) {
+        const int co = i / 18, r = i - co * 18;                      // r = c * 9 + tap
+        sw1[r * C4_C1 + co] = __ldg(P.w1 + i);
+    }
+    for (int i = tid; i < C4_C2 * C4_C1 * 9; i += C4_THREADS) {
+        const int co = i / (C4_C1 * 9), r = i - co * (C4_C1 * 9);    // r = ci * 9 + tap
+        sw2[r * C4_C2 + co] = __ldg(P.w2 + i);
+    }
 
+    // zero padding of both planes, once: every window overwrites the interiors completely and never touches the borders
+    for (int i = tid; i < 2 * IN0_H * IN0_W + C4_C1 * P1_H * P1_W; i += C4_THREADS) sm[i] = 0.f;
     for (long long win = blockIdx.x; win < n_eff; win += gridDim.x) {
-        __syncthreads();
-        for (int i = tid; i < 2 * IN0_H * IN0_W + C4_C1 * P1_H * P1_W; i += C4_THREADS) sm[i] = 0.f;
         __syncthreads();
         const float* xw = x + win * (2 * C4_T * C4_F);
         for (int i = tid; i < 2 * C4_T * C4_F; i += C4_THREADS) {
@@ -69,8 +83,10 @@ cnn4dof_conv_kernel(Cnn4Dev P, const float* __restrict__ x, const int* __restric
 
         // conv1 + BN + ReLU + 2x2 max: item = (channel group of 8, pooled position)
         for (int item = tid; item < 2 * C4_H1 * C4_W1; item += C4_THREADS) {
-            const int cg = item / (C4_H1 * C4_W1);
-            const int pos = item - cg * (C4_H1 * C4_W1);
+            // channel group fastest: the 2 lanes of a position share (broadcast) the patch loads, and a warp's 16 positions
+            // touch few shared-memory banks twice (position-major items cost 35 % of all wavefronts in bank conflicts)
+            const int cg = item & 1;
+            const int pos = item >> 1;
             const int ph = pos / C4_W1, pw = pos - ph * C4_W1;
             float patch[2][4][4];
 #pragma unroll
@@ -79,24 +95,40 @@ cnn4dof_conv_kernel(Cnn4Dev P, const float* __restrict__ x, const int* __restric
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) patch[c][r][q] = in0[(c * IN0_H + 2 * ph + r) * IN0_W + 2 * pw + q];
+            f32x2 acc2[4][4];                                        // [channel pair][2x2 pool position]
+#pragma unroll
+            for (int cp = 0; cp < 4; ++cp) { acc2[cp][0] = 0ull; acc2[cp][1] = 0ull; acc2[cp][2] = 0ull; acc2[cp][3] = 0ull; }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                f32x2 pd[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pd[r][q] = pk2(patch[c][r][q], patch[c][r][q]);
+#pragma unroll
+                for (int kr = 0; kr < 3; ++kr)
+#pragma unroll
+                    for (int kq = 0; kq < 3; ++kq) {
+                        const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(sw1 + (c * 9 + kr * 3 + kq) * C4_C1 + cg * 8);
+                        const ulonglong2 wa = wp[0], wb = wp[1];
+                        const f32x2 w[4] = {wa.x, wa.y, wb.x, wb.y};
+#pragma unroll
+                        for (int cp = 0; cp < 4; ++cp) {
+                            acc2[cp][0] = fma2(w[cp], pd[kr][kq], acc2[cp][0]);
+                            acc2[cp][1] = fma2(w[cp], pd[kr][kq + 1], acc2[cp][1]);
+                            acc2[cp][2] = fma2(w[cp], pd[kr + 1][kq], acc2[cp][2]);
+                            acc2[cp][3] = fma2(w[cp], pd[kr + 1][kq + 1], acc2[cp][3]);
+                        }
+                    }
+            }
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {
                 const int co = cg * 8 + cc;
-                float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+                float a[4], o;
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int kr = 0; kr < 3; ++kr)
-#pragma unroll
-                        for (int kq = 0; kq < 3; ++kq) {
-                            const float w = sw1[(co * 2 + c) * 9 + kr * 3 + kq];
-                            a00 = fmaf(w, patch[c][kr][kq], a00);
-                            a01 = fmaf(w, patch[c][kr][kq + 1], a01);
-                            a10 = fmaf(w, patch[c][kr + 1][kq], a10);
-                            a11 = fmaf(w, patch[c][kr + 1][kq + 1], a11);
-                        }
+                for (int j = 0; j < 4; ++j) { if (cc & 1) unpk2(acc2[cc >> 1][j], o, a[j]); else unpk2(acc2[cc >> 1][j], a[j], o); }
                 const float s = __ldg(P.a1 + co), b = __ldg(P.b1 + co);
-                const float m = fmaxf(fmaxf(fmaf(a00, s, b), fmaf(a01, s, b)), fmaxf(fmaf(a10, s, b), fmaf(a11, s, b)));
+                const float m = fmaxf(fmaxf(fmaf(a[0], s, b), fmaf(a[1], s, b)), fmaxf(fmaf(a[2], s, b), fmaf(a[3], s, b)));
                 p1[(co * P1_H + ph + 1) * P1_W + pw + 1] = fmaxf(m, 0.f);
             }
         }
@@ -104,39 +136,42 @@ cnn4dof_conv_kernel(Cnn4Dev P, const float* __restrict__ x, const int* __restric
 
         // conv2 + BN + ReLU + 2x2 max: item = (channel group of 8, pooled position)
         for (int item = tid; item < 4 * C4_H2 * C4_W2; item += C4_THREADS) {
-            const int cg = item / (C4_H2 * C4_W2);
-            const int pos = item - cg * (C4_H2 * C4_W2);
+            const int cg = item & 3;                                 // channel group fastest (see conv1)
+            const int pos = item >> 2;
             const int ph = pos / C4_W2, pw = pos - ph * C4_W2;
-            float acc[8][4];
+            f32x2 acc2[4][4];                                        // [channel pair][2x2 pool position]
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc) { acc[cc][0] = 0.f; acc[cc][1] = 0.f; acc[cc][2] = 0.f; acc[cc][3] = 0.f; }
+            for (int cp = 0; cp < 4; ++cp) { acc2[cp][0] = 0ull; acc2[cp][1] = 0ull; acc2[cp][2] = 0ull; acc2[cp][3] = 0ull; }
             for (int ci = 0; ci < C4_C1; ++ci) {
-                float patch[4][4];
+                f32x2 pd[4][4];
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) patch[r][q] = p1[(ci * P1_H + 2 * ph + r) * P1_W + 2 * pw + q];
+                    for (int q = 0; q < 4; ++q) { const float v = p1[(ci * P1_H + 2 * ph + r) * P1_W + 2 * pw + q]; pd[r][q] = pk2(v, v); }
 #pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
-                    const float* wp = sw2 + ((cg * 8 + cc) * C4_C1 + ci) * 9;
+                for (int kr = 0; kr < 3; ++kr)
 #pragma unroll
-                    for (int kr = 0; kr < 3; ++kr)
+                    for (int kq = 0; kq < 3; ++kq) {
+                        const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(sw2 + (ci * 9 + kr * 3 + kq) * C4_C2 + cg * 8);
+                        const ulonglong2 wa = wp[0], wb = wp[1];
+                        const f32x2 w[4] = {wa.x, wa.y, wb.x, wb.y};
 #pragma unroll
-                        for (int kq = 0; kq < 3; ++kq) {
-                            const float w = wp[kr * 3 + kq];
-                            acc[cc][0] = fmaf(w, patch[kr][kq], acc[cc][0]);
-                            acc[cc][1] = fmaf(w, patch[kr][kq + 1], acc[cc][1]);
-                            acc[cc][2] = fmaf(w, patch[kr + 1][kq], acc[cc][2]);
-                            acc[cc][3] = fmaf(w, patch[kr + 1][kq + 1], acc[cc][3]);
+                        for (int cp = 0; cp < 4; ++cp) {
+                            acc2[cp][0] = fma2(w[cp], pd[kr][kq], acc2[cp][0]);
+                            acc2[cp][1] = fma2(w[cp], pd[kr][kq + 1], acc2[cp][1]);
+                            acc2[cp][2] = fma2(w[cp], pd[kr + 1][kq], acc2[cp][2]);
+                            acc2[cp][3] = fma2(w[cp], pd[kr + 1][kq + 1], acc2[cp][3]);
                         }
-                }
+                    }
             }
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {
                 const int co = cg * 8 + cc;
+                float a[4], o;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { if (cc & 1) unpk2(acc2[cc >> 1][j], o, a[j]); else unpk2(acc2[cc >> 1][j], a[j], o); }
                 const float s = __ldg(P.a2 + co), b = __ldg(P.b2 + co);
-                const float m = fmaxf(fmaxf(fmaf(acc[cc][0], s, b), fmaf(acc[cc][1], s, b)),
-                                      fmaxf(fmaf(acc[cc][2], s, b), fmaf(acc[cc][3], s, b)));
+                const float m = fmaxf(fmaxf(fmaf(a[0], s, b), fmaf(a[1], s, b)), fmaxf(fmaf(a[2], s, b), fmaf(a[3], s, b)));
                 feat[win * C4_FEAT + (co * C4_H2 + ph) * C4_W2 + pw] = fmaxf(m, 0.f);
             }
         }
