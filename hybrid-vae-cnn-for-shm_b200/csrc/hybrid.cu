@@ -7,7 +7,8 @@
 
 namespace shm {
 
-constexpr long long HY_CHUNK = 65536;     // flagged windows per second-pass chunk: bounds cnn_in at 629 MB for the 4DOF shape
+constexpr long long HY_CHUNK = 75776;     // flagged windows per second-pass chunk = 4 whole waves of 128-window tiles on 148 SMs (65,536 = 3.46 waves left the
+                                          // scorer a 13 % tail per chunk); bounds cnn_in at 727 MB for the 4DOF shape
 
 struct HyLayout {
     size_t mu, lv, cnn_in, label, p, logits, cnt, compact, total;

@@ -332,7 +332,7 @@ int shm_cnnol_engine(const shm_cnnol* h);
 /* ---------------------------------------------------------------------------------------------
  * Fused hybrid loops: the reference's script-level hot loops as ONE call on one stream.  No host synchronisation:
  * the flagged count stays on the device; per-flagged scratch is bounded (the 4DOF second pass runs in chunks of
- * 65,536 flagged windows), so `max_flagged` may be as large as n.
+ * 75,776 flagged windows), so `max_flagged` may be as large as n.
  *
  * shm_hybrid4dof_score == eval_group (4DOF/Scripts/06_test_full_pipeline.py:327-383): score pass (eps1[n,Z]) ->
  *   `mse > thr` + np.where (:350-351) -> SECOND VAE pass on the flagged windows with fresh noise (eps2[j] belongs to
