@@ -747,7 +747,9 @@ int cnnol_tc_pack(CnnOlTc* t, const float* const raw_w[4], cudaStream_t st) {
 }
 
 static int ensure_workspace(CnnOlTc* t, long long n) {
-    constexpr long long kMaxChunk = 8192;
+    // 9472 = 148 * 64: with 7 tile pairs per group of 4 / 8 / 16 windows the three GEMMs get 112 / 56 / 28 whole waves of items on
+    // 148 SMs (8192 left block 4 a 25th, 20 %-filled wave)
+    constexpr long long kMaxChunk = 9472;
     long long want = n < kMaxChunk ? n : kMaxChunk;
     want = (want + 255) / 256 * 256;
     if (t->chunk >= want) return SHM_OK;

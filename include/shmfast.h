@@ -324,7 +324,7 @@ int shm_cnnol_destroy(shm_cnnol* h);
 int shm_cnnol_forward(shm_cnnol* h, const shm_window_src* src_host, const int32_t* idx, const int32_t* n_dev,
                       int64_t n, float* logits, double* prob, void* stream);
 /* Engine of the convolution blocks: SHM_ENGINE_TC_BF16X3 (default; blocks 2-4 as implicit GEMMs on the tensor cores,
- * 3-pass fp16 hi/lo split, fp32 accumulate; the first call allocates a workspace of ~0.21 MB per window for up to 8192
+ * 3-pass fp16 hi/lo split, fp32 accumulate; the first call allocates a workspace of ~0.21 MB per window for up to 9472
  * windows per internal chunk) or SHM_ENGINE_FP32 (everything on the CUDA cores, one CTA per window, no workspace). */
 int shm_cnnol_set_engine(shm_cnnol* h, int engine);
 int shm_cnnol_engine(const shm_cnnol* h);

@@ -246,17 +246,17 @@ def test_cnnol_ragged_idx_and_device_count(cuda_dev, engine):
 
 
 def test_cnnol_two_chunks_position_independent(cuda_dev):
-    """Tensor-core openLAB CNN over more windows than one internal chunk (8192) with a ragged tail: a window's logits do not depend
+    """Tensor-core openLAB CNN over more windows than one internal chunk (9472) with a ragged tail: a window's logits do not depend
     on the chunk, tile pair or producer group it lands in (the fused operand producer stages 4 / 8 / 16 windows per tile) -- a
     shuffled subset recomputed through a gather list agrees to fp32 rounding of the GroupNorm statistics, a handful with the oracle."""
     sd = synth.cnnol_weights(seed=5)
-    N = 8192 + 37
+    N = 9472 + 37
     x = synth.windows(N, 200, 4, seed=6, amp=1.5)
     cnn = ops.CnnOpenLab(sd, cuda_dev)
     src = ops.WindowSource(to_dev(x, cuda_dev), 200)
     a = cnn.forward(src)
     assert a.shape[0] == N and torch.isfinite(a).all()
-    sel = torch.cat([torch.tensor([0, 8191, 8192, N - 1]), torch.randperm(N)[:203]]).to(torch.int32).to(cuda_dev)
+    sel = torch.cat([torch.tensor([0, 9471, 9472, N - 1]), torch.randperm(N)[:203]]).to(torch.int32).to(cuda_dev)
     b = cnn.forward(src, n=int(sel.numel()), idx=sel)
     assert torch.allclose(b, a[sel.long()], rtol=1e-5, atol=1e-6)
     k = sel[:6].cpu().numpy()
