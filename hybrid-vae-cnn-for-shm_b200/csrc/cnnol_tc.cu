@@ -69,6 +69,12 @@ __device__ __forceinline__ float silu_fast(float x) {
     return x * r;
 }
 
+// packed fp32 pairs (sm_100 fma.rn.f32x2 -> FFMA2: two lanes per issue slot, same flops per clock; scripts/ffma2_probe.cu)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ long long eff_windows(long long n_total, const int* n_dev, long long base, long long n_chunk) {
@@ -108,25 +114,28 @@ __global__ void __launch_bounds__(256) ol_conv1_kernel(const float* __restrict__
         float gs = 0.f, gq = 0.f;
         const float4 bias4 = *reinterpret_cast<const float4*>(bs + cb * 4);
         for (int h = tid >> 3; h < OLT_T; h += 32) {
-            float acc[4][4];
+            // two output channels per packed FMA (fma.rn.f32x2 -> FFMA2): 24 issue slots per filter row instead of 48
+            f32x2 acc2[4][2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { acc[q][0] = bias4.x; acc[q][1] = bias4.y; acc[q][2] = bias4.z; acc[q][3] = bias4.w; }
+            for (int q = 0; q < 4; ++q) { acc2[q][0] = pk2(bias4.x, bias4.y); acc2[q][1] = pk2(bias4.z, bias4.w); }
 #pragma unroll
             for (int dt = 0; dt < 7; ++dt) {
                 const float4 xa = *reinterpret_cast<const float4*>(xin + (h + dt) * 8);
                 const float2 xb = *reinterpret_cast<const float2*>(xin + (h + dt) * 8 + 4);
-                const float xr[6] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y};
+                const f32x2 xr[6] = {pk2(xa.x, xa.x), pk2(xa.y, xa.y), pk2(xa.z, xa.z), pk2(xa.w, xa.w), pk2(xb.x, xb.x), pk2(xb.y, xb.y)};
 #pragma unroll
                 for (int df = 0; df < 3; ++df) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(wk + (dt * 3 + df) * 32 + cb * 4);
+                    const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(wk + (dt * 3 + df) * 32 + cb * 4);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float x = xr[q + df];
-                        acc[q][0] = fmaf(x, w4.x, acc[q][0]); acc[q][1] = fmaf(x, w4.y, acc[q][1]);
-                        acc[q][2] = fmaf(x, w4.z, acc[q][2]); acc[q][3] = fmaf(x, w4.w, acc[q][3]);
+                        acc2[q][0] = fma2(xr[q + df], w4.x, acc2[q][0]);
+                        acc2[q][1] = fma2(xr[q + df], w4.y, acc2[q][1]);
                     }
                 }
             }
+            float acc[4][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { unpk2(acc2[q][0], acc[q][0], acc[q][1]); unpk2(acc2[q][1], acc[q][2], acc[q][3]); }
             float* o = out + ((size_t)w * OLT_T * OLT_F + (size_t)h * OLT_F) * 32 + cb * 4;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {

@@ -56,11 +56,12 @@ window_normalize_kernel(WinSrc src, const int* __restrict__ idx, long long N, fl
 // STG.128 per 16 output bytes, one warp per window, no index divisions).  Same arithmetic (win_transform), hence the
 // same bits, as the generic kernel.
 constexpr int WT_THREADS = 256;
-constexpr int WT_SMEM_FLOATS = 11 * 1024;          // 44 KB tile (static shared memory)
+constexpr int WT_SMEM_FLOATS = 11 * 1024;          // largest tile: 44 KB of dynamic shared memory (the launch asks for what its group needs)
+constexpr int WT_TARGET_FLOATS = 6 * 1024;         // series groups are sized to <= 24 KB when that still holds >= 32 windows: 8 CTAs per SM
 
 __global__ void __launch_bounds__(WT_THREADS)
 window_tile_kernel(WinSrc src, const int* __restrict__ idx, long long N, float* __restrict__ out, int group, int step_rows) {
-    __shared__ __align__(16) float tile[WT_SMEM_FLOATS];
+    extern __shared__ __align__(16) float tile[];
     __shared__ int s_chan[SHM_MAX_D];
     const int T = src.T, D = src.D, TD = T * D;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -139,18 +140,22 @@ extern "C" int shm_window_normalize(const shm_window_src* src_host, const int32_
     if (out16 && TD <= WT_SMEM_FLOATS && w.row_stride > 0 && w.win_stride > 0 && w.win_stride % w.row_stride == 0 &&
         w.win_stride / w.row_stride < (1 << 20)) {
         const int step_rows = (int)(w.win_stride / w.row_stride);
-        int group;
+        int group, tile_floats;
         if (idx == nullptr) {                                       // consecutive windows share the staged rows
-            const int max_rows = WT_SMEM_FLOATS / w.D;
-            group = (max_rows - w.T) / step_rows + 1;
-            group = group > 128 ? 128 : group;
+            auto fit = [&](int floats) { const int g = (floats / w.D - w.T) / step_rows + 1; return g > 128 ? 128 : g; };
+            group = fit(WT_SMEM_FLOATS);
+            // a smaller tile = more resident CTAs, so one CTA's staging phase hides under the others' copy phase (openLAB,
+            // stride 20: 128-window groups in 44 KB tiles ran 5 CTAs per SM at 68 % of the copy bandwidth)
+            if (TD <= WT_TARGET_FLOATS && fit(WT_TARGET_FLOATS) >= 32) group = fit(WT_TARGET_FLOATS);
+            tile_floats = ((group - 1) * step_rows + w.T) * w.D;
         } else {                                                    // gathered windows: one slab each
             group = WT_SMEM_FLOATS / TD;
             group = group > 16 ? 16 : group;
+            tile_floats = group * TD;
         }
         const long long tgroups = (N + group - 1) / group;
         const int tgrid = (int)min(tgroups, (long long)sms * 16);
-        window_tile_kernel<<<tgrid, WT_THREADS, 0, st>>>(w, idx, N, out, group, step_rows);
+        window_tile_kernel<<<tgrid, WT_THREADS, (size_t)tile_floats * sizeof(float), st>>>(w, idx, N, out, group, step_rows);
         SHM_LAUNCH_CHECK();
         return SHM_OK;
     }
