@@ -17,6 +17,8 @@ $NCU --log-file $O/r02_launches_train.csv python scripts/prof_train.py > /dev/nu
 $NCU --log-file $O/r02_launches_cnn_train_4dof.csv python scripts/prof_cnn_train.py 4dof > /dev/null 2>&1
 $NCU --log-file $O/r02_launches_cnn_train_openlab.csv python scripts/prof_cnn_train.py openlab > /dev/null 2>&1
 $NCU --log-file $O/r02_launches_cnnol_8192.csv python scripts/prof_cnnol_ncu.py > /dev/null 2>&1
+$NCU --log-file $O/r02_percentile_launches.csv python scripts/prof_percentile.py > /dev/null 2>&1
+python scripts/membound_bench.py > $O/r02_membound.jsonl 2>/dev/null
 python scripts/launch_summary.py $O/r02_launches_*.csv > $O/r02_launch_summary.txt 2>&1
 FULL="ncu --set full --import-source on --clock-control none"
 $FULL -k regex:ol_conv_gemm_kernel -s 3 -c 3 -o $O/r02_cnnol_fused python scripts/prof_cnnol_ncu.py > /dev/null 2>&1
