@@ -157,12 +157,21 @@ __device__ __forceinline__ void lstm_cell2(f32x2 ai, f32x2 af, f32x2 ag, f32x2 a
     unpk2(h, h0, h1);
 }
 
+// chunk loop of the epilogue passes: 1 = rolled (the cell state rotates through the register arrays: ~45 moves per 290-instruction
+// chunk), 2 = two chunks per iteration (accumulator buffer c & 1 static, half the moves), 4 = fully unrolled.  Same-box A/B at the
+// power cap, 2^20 windows: 1 -> 4.44 M, 2 -> 4.47 M, 4 -> 4.38 M windows/s (4 x 290 instructions x 4 pass bodies press on the
+// 32 KB instruction cache again); scripts/ab_unroll.sh.
+#ifndef TC_EPI_UNROLL
+#define TC_EPI_UNROLL 2
+#endif
+constexpr int kTcEpiUnroll = TC_EPI_UNROLL;
+
 // optional role profiling (TcDev.dbg != nullptr): cycles the MMA issuer spends in each kind of wait
 #define TC_TWAIT(slot, bar, par)                                   \
     do {                                                           \
-        const long long _t0 = clock64();                           \
+        const long long _t0 = TC_CLOCK();                           \
         mbar_wait(bar, par);                                       \
-        prof[slot] += clock64() - _t0;                             \
+        prof[slot] += TC_CLOCK() - _t0;                             \
     } while (0)
 
 // mbarrier use-counters: two buffers each; (b ? n1 : n0) keeps them in registers
@@ -198,9 +207,9 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& x, int c, uint32_t acc_p
     static_assert(TC_UPT == 8, "one batch of 8 units per thread per chunk");
     const int b = c & 1;
     {
-        const long long tw0 = clock64();
+        const long long tw0 = TC_CLOCK();
         mbar_wait(&x.bars->acc_full[b], acc_parity);
-        x.prof[0] += clock64() - tw0;
+        x.prof[0] += TC_CLOCK() - tw0;
     }
     tc_fence_after_sync();
     const int u0 = c * 32 + x.wg * 8;                                // first hidden unit of this thread's slice
@@ -304,7 +313,7 @@ __device__ __forceinline__ void epi_pass(const PassCtx& pc, const VaeDev& P, con
         const uint32_t hbuf = pc.t_h + (uint32_t)((t & 1) * H);
         EpiCtx ctx{pc.bars, pc.t_acc, hbuf, lane_base, pc.bias_s, pc.scratch + (size_t)t * S::IMG,
                    reinterpret_cast<float*>(pc.inbuf + pc.hT_buf * S::IMG), pc.inbuf, wg, row, lane, t == T - 1, t == 0, prof};
-#pragma unroll 1
+#pragma unroll kTcEpiUnroll
         for (int c = 0; c < NCH; ++c) {
             const uint32_t par = ((c & 1) ? nacc1 : nacc0) & 1;
             if (c & 1) ++nacc1; else ++nacc0;
@@ -689,9 +698,9 @@ __device__ __forceinline__ void aux_stage_pass(const PassCtx& pc, const VaeDev& 
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-        const long long tw0 = clock64();
+        const long long tw0 = TC_CLOCK();
         mbar_wait(&bars->in_empty[b], (n_in.get(b) & 1) ^ 1);
-        prof[0] += clock64() - tw0;
+        prof[0] += TC_CLOCK() - tw0;
         n_in.inc(b);
         unsigned char* xhi = pc.inbuf + b * 2 * TC_XSTAGE;
         unsigned char* xlo = xhi + TC_XSTAGE;
@@ -734,9 +743,9 @@ __device__ __forceinline__ void aux_out_pass(const PassCtx& pc, const VaeDev& P,
         float x[SHM_MAX_D];                                    // issued before the wait so the latency is hidden
 #pragma unroll
         for (int d = 0; d < SHM_MAX_D; ++d) x[d] = (ok && d < P.D) ? ld_nc_volatile(wbase + (long long)t * src.row_stride + src.chan[d]) : 0.f;
-        const long long tw0 = clock64();
+        const long long tw0 = TC_CLOCK();
         mbar_wait(&bars->xhat_full, n_x & 1);
-        prof[0] += clock64() - tw0;
+        prof[0] += TC_CLOCK() - tw0;
         ++n_x;
         tc_fence_after_sync();
         uint32_t acc[16];
@@ -965,7 +974,7 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
                 if (p == TC.L) heads_stage<H>(pc, P, io);
                 cta_sync();                        // (A) previous pass / heads complete and visible
                 if (p == TC.L && encode_only_call) break;
-                const long long pass_t0 = clock64();
+                const long long pass_t0 = TC_CLOCK();
                 if (in_kind == IN_HOIST) {
                     epi_hoist_pre<H>(pc, TC.pass[p].bias, acc_base);
                     cta_sync();                    // (A2) G is in global memory and the u image is dead: the input buffers now stage G
@@ -976,7 +985,7 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
                 } else if (sink == SINK_STREAM) epi_pass<H, SINK_STREAM>(pc, P, src, io, TC.pass[p].bias, acc_base, prof);
                 else if (sink == SINK_LAST_ENC) epi_pass<H, SINK_LAST_ENC>(pc, P, src, io, TC.pass[p].bias, acc_base, prof);
                 else epi_pass<H, SINK_LAST_DEC>(pc, P, src, io, TC.pass[p].bias, acc_base, prof);
-                { const long long _d = clock64() - pass_t0; const int _q = p & 3;
+                { const long long _d = TC_CLOCK() - pass_t0; const int _q = p & 3;
                   if (_q == 0) prof[4] += _d; else if (_q == 1) prof[5] += _d; else if (_q == 2) prof[6] += _d; else prof[7] += _d; }
                 cta_sync();                        // (B) end of pass
                 pass_advance(in_kind, sink);
@@ -1004,22 +1013,22 @@ vae_score_tc_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
                     cta_sync();                    // (A2)
                     if (warp == TC_WARP_PROD) { if (lane == 0) prod_hoist<H>(pc, TC.pass[p].w, ring2, false, g_base); }
                     else if (warp == TC_WARP_MMA) {
-                        const long long pass_t0 = clock64();
+                        const long long pass_t0 = TC_CLOCK();
                         mma_pass_hoist<H>(pc, ring2, acc2, h_base, prof);
-                        { const long long _d = clock64() - pass_t0; const int _q = p & 3;
+                        { const long long _d = TC_CLOCK() - pass_t0; const int _q = p & 3;
                           if (_q == 0) prof[4] += _d; else if (_q == 1) prof[5] += _d; else if (_q == 2) prof[6] += _d; else prof[7] += _d; }
                     }
                 } else if (warp == TC_WARP_PROD) {
                     if (lane == 0) prod_pass<H>(pc, TC.pass[p].w, in_kind, sink == SINK_LAST_DEC, ring_base, in_base);
                 } else if (warp == TC_WARP_MMA) {
-                    const long long pass_t0 = clock64();
+                    const long long pass_t0 = TC_CLOCK();
                     if (sink == SINK_LAST_DEC) {
                         if (in_kind == IN_STREAM) mma_pass<H, IN_STREAM, true>(pc, ring_base, in_base, acc_base, h_base, xhat_base, prof);
                         else mma_pass<H, IN_CONST, true>(pc, ring_base, in_base, acc_base, h_base, xhat_base, prof);
                     } else if (in_kind == IN_X) mma_pass<H, IN_X, false>(pc, ring_base, in_base, acc_base, h_base, xhat_base, prof);
                     else if (in_kind == IN_STREAM) mma_pass<H, IN_STREAM, false>(pc, ring_base, in_base, acc_base, h_base, xhat_base, prof);
                     else mma_pass<H, IN_CONST, false>(pc, ring_base, in_base, acc_base, h_base, xhat_base, prof);
-                    { const long long _d = clock64() - pass_t0; const int _q = p & 3;
+                    { const long long _d = TC_CLOCK() - pass_t0; const int _q = p & 3;
                   if (_q == 0) prof[4] += _d; else if (_q == 1) prof[5] += _d; else if (_q == 2) prof[6] += _d; else prof[7] += _d; }
                 } else if (warp >= TC_WARP_AUX0 && warp < TC_WARP_AUX0 + 4) {
                     if (in_kind == IN_X) aux_stage_pass(pc, P, src, io, in_base, prof);

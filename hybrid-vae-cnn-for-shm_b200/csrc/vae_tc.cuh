@@ -3,6 +3,15 @@
 #pragma once
 #include "vae_fp32.cuh"
 
+// Role counters (cycles each warp role spends waiting / working; shm_vae_debug_counters) are compiled in only with -DSHM_TC_PROF
+// (SHMFAST_PROF=1 python -m shmfast.build --force): clock64() is volatile, so the always-on form kept 8 x 64-bit counters in every
+// thread's 80-register budget and ~20 extra instructions per chunk in the epilogue's hot loop.
+#ifdef SHM_TC_PROF
+#define TC_CLOCK() clock64()
+#else
+#define TC_CLOCK() 0LL
+#endif
+
 namespace shm {
 
 struct VaeTcRaw {

@@ -67,6 +67,14 @@ __device__ __forceinline__ int d2_hT_unit(int tl) { return tl == 0 ? 5 : 3; }
 // (Measured alternatives, profiles/experiments: one 8-warp group per tile running out of phase, with one or two issuer
 // warps and per-K-block h barriers, were 6-10 % slower: the groups fall into phase through the shared tensor pipe.)
 // dec == false: encoder (keeps the fp32 h_T of the last step per tile); dec == true: decoder (h_t only feeds TMEM).
+// D2_EPI_UNROLL = 1: the (chunk, tile) loop stays rolled and the cell state rotates through the register arrays (44 of the loop's
+// 316 instructions are those moves); 4: fully unrolled, the rotation is register renaming, the body is 4x the code.  Measured equal
+// (8.20 vs 8.18 ms per 151,552 windows; 10.91 vs 10.89 M windows/s at 2^20): the pass is bound by the XU (56 MUFU per chunk and warp),
+// not by issue slots, so the rolled form stays.
+#ifndef D2_EPI_UNROLL
+#define D2_EPI_UNROLL 1
+#endif
+constexpr int kD2EpiUnroll = D2_EPI_UNROLL;
 template <bool DEC>
 __device__ __forceinline__ void d2_epi_pass(const D2Ctx& cx, const float* bias_g, uint32_t (&n_acc)[D2_NT], uint32_t (&n_xe)[D2_NT],
                                             long long (&prof)[8]) {
@@ -87,13 +95,13 @@ __device__ __forceinline__ void d2_epi_pass(const D2Ctx& cx, const float* bias_g
         for (int u = 0; u < TC_UPT; ++u) cst[v][u] = 0.f;
     const int T = cx.T;
     for (int t = 0; t < T; ++t) {
-#pragma unroll 1
+#pragma unroll kD2EpiUnroll
         for (int v = 0; v < D2_NCH * D2_NT; ++v) {
             const int c = v >> 1, tl = v & 1;
-            const long long q0 = clock64();
+            const long long q0 = TC_CLOCK();
             mbar_wait(&cx.bars->acc_full[tl], n_acc[tl] & 1);
             ++n_acc[tl];
-            const long long q1 = clock64();
+            const long long q1 = TC_CLOCK();
             tc_fence_after_sync();
             const int u0 = c * 32 + wg * 8;
             uint32_t g0[8], g1[8], g2[8], g3[8];
@@ -103,7 +111,7 @@ __device__ __forceinline__ void d2_epi_pass(const D2Ctx& cx, const float* bias_g
             tmem_ld8(abase + 64, g2);
             tmem_ld8(abase + 96, g3);
             tmem_ld_wait();
-            const long long q2 = clock64();
+            const long long q2 = TC_CLOCK();
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&cx.bars->acc_empty[tl]);
@@ -117,7 +125,7 @@ __device__ __forceinline__ void d2_epi_pass(const D2Ctx& cx, const float* bias_g
                                 __uint_as_float(g2[u]), __uint_as_float(g2[u + 1]), __uint_as_float(g3[u]), __uint_as_float(g3[u + 1]), B4,
                                 cst[0][u], cst[0][u + 1], hv[u], hv[u + 1]);
             }
-            const long long q3 = clock64();
+            const long long q3 = TC_CLOCK();
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) split_f16x2(hv[2 * j], hv[2 * j + 1], hi[j], lo[j]);
@@ -140,7 +148,7 @@ __device__ __forceinline__ void d2_epi_pass(const D2Ctx& cx, const float* bias_g
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&cx.bars->h_full[tl]);
             }
-            const long long q4 = clock64();
+            const long long q4 = TC_CLOCK();
             prof[0] += q1 - q0; prof[1] += q2 - q1; prof[2] += q3 - q2; prof[3] += q4 - q3;
             // rotate the cell state: the next (chunk, tile) moves to cst[0]
 #pragma unroll
@@ -195,11 +203,11 @@ __device__ __forceinline__ void d2_mma_pass(const D2Ctx& cx, uint32_t& n_w, uint
         __syncwarp();
     };
     {                                                       // the pass's weights have landed (once per tile pair)
-        const long long m0 = clock64();
+        const long long m0 = TC_CLOCK();
         for (int c = 0; c < D2_NCH; ++c) mbar_wait(&bars->w_full[c], n_w & 1);
         ++n_w;
         tc_fence_after_sync();
-        mp[PB + 0] += clock64() - m0;
+        mp[PB + 0] += TC_CLOCK() - m0;
     }
     for (int t = 0; t < T; ++t) {
         const uint32_t hpar = (hb + (uint32_t)(t - 1)) & 1;                            // h_full[*] of step t-1
@@ -211,11 +219,11 @@ __device__ __forceinline__ void d2_mma_pass(const D2Ctx& cx, uint32_t& n_w, uint
             for (int tl = 0; tl < D2_NT; ++tl) {
                 const uint32_t acc = d2_acc(tbase, tl);
                 // input part: needs the drained accumulator (use 2t+c of acc_empty) and, encoder chunk 0, the staged window tile
-                long long m0 = clock64();
+                long long m0 = TC_CLOCK();
                 mbar_wait(&bars->acc_empty[tl], (uint32_t)(c ^ 1));
                 if (!DEC && c == 0) mbar_wait(&bars->in_full[tl][t & 1], ipar);
                 tc_fence_after_sync();
-                { const long long m1 = clock64(); mp[PB + 2] += m1 - m0; m0 = m1; }
+                { const long long m1 = TC_CLOCK(); mp[PB + 2] += m1 - m0; m0 = m1; }
                 if (elect_one()) {
                     if (!DEC) {
                         const uint32_t a_hi = in_lo + tl * (D2_XT / 16) + (t & 1) * (2 * TC_XSTAGE / 16), a_lo = a_hi + TC_XSTAGE / 16;
@@ -239,7 +247,7 @@ __device__ __forceinline__ void d2_mma_pass(const D2Ctx& cx, uint32_t& n_w, uint
                 if (c == 0 && t > 0) {
                     mbar_wait(&bars->h_full[tl], hpar);
                     tc_fence_after_sync();
-                    mp[PB + 1] += clock64() - m0;
+                    mp[PB + 1] += TC_CLOCK() - m0;
                 }
                 if (elect_one()) {
                     if (t > 0) {                            // A = h_{t-1} (hi|lo) from TMEM
@@ -461,7 +469,7 @@ vae_score_tc_dual_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             set_pair(pair);
             cta_sync();                                    // (A) encoder pass
-            { const long long p0 = clock64(); d2_epi_pass<false>(cx, TC.pass[0].bias, e_acc, e_xe, prof); prof[4] += clock64() - p0; }
+            { const long long p0 = TC_CLOCK(); d2_epi_pass<false>(cx, TC.pass[0].bias, e_acc, e_xe, prof); prof[4] += TC_CLOCK() - p0; }
             cta_sync();                                    // (B)
             for (int tl = 0; tl < D2_NT; ++tl) {           // heads, one tile after the other
                 PassCtx pc;
@@ -474,7 +482,7 @@ vae_score_tc_dual_kernel(VaeDev P, TcDev TC, WinSrc src, VaeIO io) {
             }
             cta_sync();                                    // (C) decoder pass
             if (encode_only_call) continue;
-            { const long long p0 = clock64(); d2_epi_pass<true>(cx, TC.pass[1].bias, e_acc, e_xe, prof); prof[5] += clock64() - p0; }
+            { const long long p0 = TC_CLOCK(); d2_epi_pass<true>(cx, TC.pass[1].bias, e_acc, e_xe, prof); prof[5] += TC_CLOCK() - p0; }
             cta_sync();                                    // (D)
         }
         if (TC.dbg && tid == 0) for (int i = 0; i < 8; ++i) TC.dbg[(blockIdx.x * 3 + 2) * 8 + i] = prof[i];

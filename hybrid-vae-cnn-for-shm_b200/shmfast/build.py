@@ -19,6 +19,9 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
 ]
+if os.environ.get("SHMFAST_PROF") == "1":          # role counters of the tensor-core scorers (csrc/vae_tc.cuh); part of the digest
+    NVCC_FLAGS.append("-DSHM_TC_PROF")
+NVCC_FLAGS += os.environ.get("SHMFAST_NVCC_EXTRA", "").split()          # experiment knobs (-D...), part of the digest
 
 
 def nvcc() -> str:

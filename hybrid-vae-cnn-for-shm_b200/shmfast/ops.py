@@ -249,7 +249,8 @@ class VaeScorer:
         return out
 
     def debug_counters(self, n_cta: int = 148):
-        """Tensor-core engine profiling counters [n_cta, 8] (first call enables them)."""
+        """Tensor-core engine profiling counters [n_cta, 3 roles, 8] (first call enables them); all zero unless the library was
+        built with SHMFAST_PROF=1 (the counters cost registers and issue slots in the hot loops, so they are compiled out by default)."""
         buf = np.zeros((n_cta, 3, 8), dtype=np.int64)     # roles: MMA issuer, window-staging warp, epilogue warp 0
         check(self._lib.shm_vae_debug_counters(self._h, buf.ctypes.data_as(C.c_void_p), buf.size), "shm_vae_debug_counters")
         return buf

@@ -131,7 +131,8 @@ int shm_vae_engine(const shm_vae* h);    /* the engine actually selected */
 int shm_vae_get_cfg(const shm_vae* h, shm_vae_cfg* out_host);   /* the handle's shape; engine = the one selected */
 /* Profiling aid (tensor-core engine): the first call enables per-CTA cycle counters of the MMA-issuer warp,
  * later calls copy them out: out_host[cta*8 + {0: wait weights, 1: wait input, 2: wait accumulator drain,
- * 3: wait h_t, 4..7: total cycles of pass 0..3}], accumulated over launches. */
+ * 3: wait h_t, 4..7: total cycles of pass 0..3}], accumulated over launches.  The counters are compiled into the kernels only
+ * when the library is built with -DSHM_TC_PROF (SHMFAST_PROF=1 python -m shmfast.build --force); the default build returns zeros. */
 int shm_vae_debug_counters(shm_vae* h, long long* out_host, int n);
 
 /* Fused forward + score for n windows: encode -> z = mu + eps*exp(0.5*logvar) -> decode ->

@@ -14,6 +14,8 @@ e0.record(); vae.score(src, eps); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 c = vae.debug_counters()
 print(f"N={N} {ms:.2f} ms -> {N/ms*1e3/1e6:.3f} M windows/s")
+if not c.any():
+    print("role counters are compiled out (build with SHMFAST_PROF=1 python -m shmfast.build --force to get them)"); sys.exit(0)
 m = c.mean(0) / 1e6
 print("MMA issuer : wait weights %.2f  input %.2f  acc drain %.2f  h %.2f | pass totals %s" % (m[0,0], m[0,1], m[0,2], m[0,3], np.round(m[0,4:], 2)))
 print("aux warp 8 : wait (in_empty / xhat_full) %.2f" % (m[1,0],))
