@@ -45,7 +45,9 @@ constexpr int TC_THREADS = (TC_EPI_WARPS + 8) * 32;   // epilogue | staging/outp
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_CLUSTER = 2;                 // CTAs per cluster: each loads half of every weight stage and multicasts it to both
 constexpr int TC_HEADS_SCRATCH = 3 * 16 * 128 * 4;   // per-CTA global scratch of the heads stage (mu | logvar | z), bytes
-constexpr int TC_REG_EPI = 88, TC_REG_AUX = 64;       // setmaxnreg budgets: 16*32*88 + 8*32*64 = 61440 of 65536 registers
+// setmaxnreg budgets: 16*32*88 + 8*32*64 = 61440 of 65536 registers.  Do not raise the epilogue's share: 96 / 56 (63,488 in total, one
+// spill pair less in the epilogue loops) DEAD-LOCKED the kernel on the B200 -- like the budgets that added up to exactly 65,536 before it.
+constexpr int TC_REG_EPI = 88, TC_REG_AUX = 64;
 constexpr float NLOG2E = -1.4426950408889634f;
 
 enum { IN_X = 0, IN_STREAM = 1, IN_CONST = 2, IN_HOIST = 3 };

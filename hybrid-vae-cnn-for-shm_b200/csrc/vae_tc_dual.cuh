@@ -94,13 +94,13 @@ __device__ __forceinline__ void d2_epi_pass(const D2Ctx& cx, const float* bias_g
 #pragma unroll
         for (int u = 0; u < TC_UPT; ++u) cst[v][u] = 0.f;
     const int T = cx.T;
+    const uint32_t pa0 = n_acc[0], pa1 = n_acc[1], px0 = n_xe[0], px1 = n_xe[1];     // barrier phases at the start of the pass
     for (int t = 0; t < T; ++t) {
 #pragma unroll kD2EpiUnroll
         for (int v = 0; v < D2_NCH * D2_NT; ++v) {
             const int c = v >> 1, tl = v & 1;
             const long long q0 = TC_CLOCK();
-            mbar_wait(&cx.bars->acc_full[tl], n_acc[tl] & 1);
-            ++n_acc[tl];
+            mbar_wait(&cx.bars->acc_full[tl], ((tl ? pa1 : pa0) + (uint32_t)c) & 1);     // use 2t + c of the pass: no counter in local memory
             const long long q1 = TC_CLOCK();
             tc_fence_after_sync();
             const int u0 = c * 32 + wg * 8;
@@ -131,8 +131,7 @@ __device__ __forceinline__ void d2_epi_pass(const D2Ctx& cx, const float* bias_g
             for (int j = 0; j < 4; ++j) split_f16x2(hv[2 * j], hv[2 * j + 1], hi[j], lo[j]);
             const uint32_t hbuf = d2_h(cx.tbase, tl, t & 1) + lane_base;
             if (DEC && c == 1 && t > 0) {                       // columns [16,32) still carry xhat_{t-1} until it has been read
-                mbar_wait(&cx.bars->xhat_empty[tl], n_xe[tl] & 1);
-                ++n_xe[tl];
+                mbar_wait(&cx.bars->xhat_empty[tl], ((tl ? px1 : px0) + (uint32_t)(t - 1)) & 1);
                 tc_fence_after_sync();
             }
             tmem_st4(hbuf + (uint32_t)(u0 >> 1), hi);
@@ -158,7 +157,8 @@ __device__ __forceinline__ void d2_epi_pass(const D2Ctx& cx, const float* bias_g
             }
         }
     }
-    if (DEC) { ++n_xe[0]; ++n_xe[1]; }                          // xhat_{T-1}: read before the pass-end barrier, never waited for here
+    n_acc[0] += (uint32_t)(D2_NCH * T); n_acc[1] += (uint32_t)(D2_NCH * T);
+    if (DEC) { n_xe[0] += (uint32_t)T; n_xe[1] += (uint32_t)T; }       // T - 1 waits + xhat_{T-1}: read before the pass-end barrier, never waited for here
 }
 
 // ------------------------------------------------------------------------------------------------ MMA issuer warp
