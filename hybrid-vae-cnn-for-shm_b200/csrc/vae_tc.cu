@@ -122,6 +122,23 @@ __device__ __forceinline__ f32x2 ex2_2(float x0, float x1, float clampv) {
     return pk2(ex2_approx(fminf(x0, clampv)), ex2_approx(fminf(x1, clampv)));
 }
 __device__ __forceinline__ f32x2 rcp_2(f32x2 v) { float a, b; unpk2(v, a, b); return pk2(rcp_approx(a), rcp_approx(b)); }
+// 1/x0, 1/x1 from ONE reciprocal: r = rcp(x0*x1), 1/x0 = r*x1, 1/x1 = r*x0 (1 MUFU + 3 FMUL instead of 2 MUFU).  Only for the
+// h = (2-q) / ((1+e_o) q) denominators: they are >= 1 (no underflow) and <= 2^73, so the product overflows (r = 0, both h = 0) only
+// when each exceeds 2^55, i.e. 1+e_o >= 2^25 and the true |h| < 2^-25 for both cells.  Not for c' = num / (P b): there a saturated
+// input + cell gate with an OPEN forget gate makes P b huge while c' = c is not small.
+#ifndef SHM_PAIR_RCP_H
+#define SHM_PAIR_RCP_H 0
+#endif
+__device__ __forceinline__ f32x2 rcp_pair(f32x2 v) {
+#if SHM_PAIR_RCP_H
+    float a, b;
+    unpk2(v, a, b);
+    const float r = rcp_approx(a * b);
+    return pk2(r * b, r * a);
+#else
+    return rcp_2(v);
+#endif
+}
 // gate arguments of units (u, u+1); B4 = multipliers {Bi(u),Bi(u+1)}, {Bf..}, {Bg..}, {Bo..}; c, h in/out for both units
 __device__ __forceinline__ void lstm_cell_bmul2(float ai0, float ai1, float af0, float af1, float ag0, float ag1, float ao0, float ao1,
                                                 const f32x2 (&B4)[4], float& c0, float& c1, float& h0, float& h1) {
@@ -136,7 +153,7 @@ __device__ __forceinline__ void lstm_cell_bmul2(float ai0, float ai1, float af0,
     float k0, k1;
     unpk2(mul2(c, k2), k0, k1);
     const f32x2 q = add2(ex2_2(k0, k1, 30.f), one);
-    const f32x2 h = mul2(fma2(q, m1, two), rcp_2(mul2(fma2(eo, B4[3], one), q)));
+    const f32x2 h = mul2(fma2(q, m1, two), rcp_pair(mul2(fma2(eo, B4[3], one), q)));
     unpk2(h, h0, h1);
 }
 
@@ -155,7 +172,7 @@ __device__ __forceinline__ void lstm_cell2(f32x2 ai, f32x2 af, f32x2 ag, f32x2 a
     unpk2(c, c0, c1);
     unpk2(mul2(c, k2), x0, x1);
     const f32x2 q = add2(ex2_2(x0, x1, 30.f), one);
-    const f32x2 h = mul2(fma2(q, m1, two), rcp_2(mul2(o, q)));
+    const f32x2 h = mul2(fma2(q, m1, two), rcp_pair(mul2(o, q)));
     unpk2(h, h0, h1);
 }
 
